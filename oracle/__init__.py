@@ -1,0 +1,4 @@
+"""CPU oracle (TEST INFRASTRUCTURE ONLY) — see oracle/tpd_oracle.h.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""

@@ -1,0 +1,11 @@
+"""torpedo_b200 — B200-native (sm_100a) implementation of ndming/torpedo's Gaussian-splatting forward rasterizer.
+
+Product layers:
+  include/tpdcu.h + torpedo_b200/csrc/     hand-written CUDA kernels behind a C ABI (lib/libtpdcu.so)
+  include/torpedo_b200/*.hpp               Vulkan-free C++ drop-in of tpd::GaussianEngine & friends
+  torpedo_b200/{_lib,engine}.py            ctypes mirror of the same interface (tests, bench)
+There is no CPU fallback: importing works anywhere, but every call needs the built library and an sm_100 GPU.
+"""
+from .engine import Camera, GaussianEngine, PerspectiveCamera, Scene, Settings, TpdError  # noqa: F401
+
+__all__ = ["Camera", "GaussianEngine", "PerspectiveCamera", "Scene", "Settings", "TpdError"]

@@ -1,0 +1,160 @@
+// common.cuh — shared device/host declarations of libtpdcu (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tpdcu {
+
+constexpr uint32_t TILE_PX = 16;          // BLOCK_X == BLOCK_Y (reference GaussianEngine.h:122-123)
+constexpr uint32_t PRE_THREADS = 256;     // Gaussians per preprocess partition (one per thread)
+constexpr uint32_t SH_PLANES = 12;        // 48 SH floats as 12 float4 planes
+constexpr uint32_t SORT_RADIX_BITS = 8;
+constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
+constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
+constexpr uint32_t SORT_THREADS = 512;
+constexpr uint32_t SORT_KPT = 8;          // keys per thread
+constexpr uint32_t SORT_TILE = SORT_THREADS * SORT_KPT;
+constexpr uint32_t SORT_WARPS = SORT_THREADS / 32;
+
+// Per-frame control block; lives at the head of the per-frame zeroed region.
+struct FrameCtl {
+    uint32_t scan_ticket;                 // preprocess partition tickets
+    uint32_t pairs_total;                 // P (tilesRendered), may exceed capacity
+    uint32_t visible;                     // Gaussians with tiles > 0
+    uint32_t pad0;
+    uint32_t sort_ticket[SORT_MAX_PASSES];
+    uint32_t hist[SORT_MAX_PASSES][SORT_BINS];  // global digit histograms (then exclusive offsets)
+};
+
+// Written by the plan kernel, read by every sort pass and by the consumers of the sorted pairs.
+struct SortPlan {
+    uint32_t n;                           // number of pairs to sort (min(P, capacity))
+    uint32_t num_passes;
+    uint32_t final_sel;                   // which ping-pong buffer holds the result
+    uint32_t passes_run;
+    uint32_t skip[SORT_MAX_PASSES];       // pass is an identity permutation (single occupied bin)
+    uint32_t src_sel[SORT_MAX_PASSES];    // ping-pong buffer the pass reads from
+};
+
+// Camera-derived constants, produced once per frame by the setup kernel.
+struct FrameCam {
+    float V[16];                          // view matrix, row-major
+    float focal[2];                       // 0.5 * size * focalNDC (project.slang:55)
+    float cam_pos[3];                     // getCameraWorldPosition (splat/common.slang:88-92)
+    float pad[3];
+};
+
+// Internal splat record (48 B): the reference's Splat (splat.slang:33-39) permuted so that the
+// blend stage's always-needed 6 floats come first.
+struct __align__(16) SplatRec {
+    float px, py, conic_a, conic_b;       // float4 #0
+    float conic_c, opacity, view_z, radius; // float4 #1
+    float r, g, b, pad;                   // float4 #2
+};
+static_assert(sizeof(SplatRec) == 48, "SplatRec must be 48 bytes");
+
+struct SceneArrays {
+    const float4* posop;                  // xyz + opacity
+    const float4* cov_a;                  // S00 S01 S02 S11
+    const float2* cov_b;                  // S12 S22
+    const float4* sh;                     // [SH_PLANES][n], float index f = 3*coef + channel
+    const uint32_t* entity;               // nullptr when the scene has a single entity
+    uint32_t n;
+    uint32_t entity_count;
+};
+
+// Lookback descriptor states (both the preprocess scan and the onesweep passes)
+constexpr uint32_t FLAG_INVALID = 0u;
+constexpr uint32_t FLAG_AGGREGATE = 1u;
+constexpr uint32_t FLAG_PREFIX = 2u;
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ---- host-side launchers (one per translation unit) ---------------------------------------------
+
+struct PreprocessLaunch {
+    SceneArrays scene;
+    const float* models;                  // device, entity_count x 16
+    FrameCam* cam;                        // device scratch
+    float* vm;                            // device scratch, entity_count x 16
+    float* pm;                            // device scratch, entity_count x 16
+    FrameCtl* ctl;
+    uint64_t* scan_desc;                  // zeroed, one per partition
+    SplatRec* recs;
+    uint32_t* offsets;                    // exclusive pair offset per Gaussian (n + 1 entries)
+    uint64_t* keys;
+    uint32_t* vals;
+    uint32_t capacity;
+    uint32_t width, height, sh_degree;
+};
+struct CameraUbo { float f[34]; };          // the reference's 136-byte Camera block, passed by value
+cudaError_t launch_setup(const PreprocessLaunch& a, const CameraUbo& ubo, cudaStream_t s);
+cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s);
+
+struct CompileLaunch {
+    const float* recs240;                 // device, n x 60 floats
+    float4* posop;
+    float4* cov_a;
+    float2* cov_b;
+    float4* sh;
+    uint32_t n;
+};
+cudaError_t launch_compile_scene(const CompileLaunch& a, cudaStream_t s);
+
+struct SortLaunch {
+    uint64_t* keys[2];
+    uint32_t* vals[2];
+    FrameCtl* ctl;
+    SortPlan* plan;
+    uint32_t* lookback;                   // zeroed, [num_passes][parts_cap][SORT_BINS]
+    uint32_t capacity;                    // launch bound for grids
+    uint32_t end_bit;
+    int sm_count;
+};
+// n is taken from ctl->pairs_total clamped to capacity (frame path) when n_host == UINT32_MAX,
+// else from n_host (standalone sort).
+cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cudaEvent_t ev_after_plan);
+uint32_t sort_parts(uint32_t capacity);
+
+struct RasterLaunch {
+    const uint64_t* keys[2];
+    const uint32_t* vals[2];
+    const SortPlan* plan;
+    const SplatRec* recs;
+    uint32_t* ranges;                     // zeroed, tiles x 2
+    uint8_t* out;
+    size_t pitch;
+    uint32_t capacity;
+    uint32_t width, height;
+};
+cudaError_t launch_ranges(const RasterLaunch& a, cudaStream_t s);
+cudaError_t launch_blend(const RasterLaunch& a, cudaStream_t s);
+
+cudaError_t launch_sort_copy_result(const SortLaunch& a, uint64_t* out_keys, uint32_t* out_vals, uint32_t n, cudaStream_t s);
+
+cudaError_t launch_export_splats(const SplatRec* recs, const uint32_t* offsets, uint32_t n, void* out48, cudaStream_t s);
+
+}  // namespace tpdcu

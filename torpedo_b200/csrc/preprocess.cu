@@ -1,0 +1,419 @@
+// preprocess.cu — scene compilation, per-frame camera setup, and the fused
+// project + exclusive-scan + tile-key duplication kernel.
+//
+// COMPILED WITH --fmad=false: everything that feeds a key, a tile count or a range must be evaluated in
+// fp32, in the written order, with no contraction, exactly like oracle/tpd_oracle.c (SURVEY.md §8a
+// "bit-critical chain"). sqrt, division and ceil are IEEE-correct with nvcc's defaults.
+//
+// Replaces, in one launch per frame and with no host read-back of P:
+//   project.slang:33-106  (cull, view/clip transform, EWA covariance, conic, radius, rect, SH colour)
+//   prefix.slang:38-159   (exclusive scan of the tile counts; decoupled look-back)
+//   keygen.slang:21-53    (one (tile|depth, index) pair per overlapped tile)
+//   GaussianEngine.cpp:662-674 (the mid-frame fence wait + read of tilesRendered is gone)
+#include "common.cuh"
+
+namespace tpdcu {
+
+// ---------------------------------------------------------------------------------------------------
+// scene compilation: 240-byte AoS records -> planar arrays + camera-independent 3D covariance
+// (splat/volume.slang:20-41 computeCovariance, evaluated once instead of once per frame)
+// ---------------------------------------------------------------------------------------------------
+
+constexpr uint32_t COMPILE_THREADS = 128;
+
+__global__ void __launch_bounds__(COMPILE_THREADS) compile_scene_kernel(CompileLaunch a) {
+    __shared__ float4 stage[COMPILE_THREADS * 15];  // 128 records x 240 B
+    const uint32_t base = blockIdx.x * COMPILE_THREADS;
+    const uint32_t count = min(COMPILE_THREADS, a.n - base);
+    const float4* src = reinterpret_cast<const float4*>(a.recs240) + (size_t)base * 15;
+    for (uint32_t k = threadIdx.x; k < count * 15; k += COMPILE_THREADS) stage[k] = src[k];
+    __syncthreads();
+    if (threadIdx.x >= count) return;
+    const float* g = reinterpret_cast<const float*>(stage) + threadIdx.x * 60;
+    const uint32_t i = base + threadIdx.x;
+
+    const float qx = g[4], qy = g[5], qz = g[6], qw = g[7];
+    const float sx = g[8] * g[11], sy = g[9] * g[11], sz = g[10] * g[11];
+    const float R[9] = {
+        1.0f - 2.0f * (qy * qy + qz * qz), 2.0f * (qx * qy - qw * qz),        2.0f * (qx * qz + qw * qy),
+        2.0f * (qx * qy + qw * qz),        1.0f - 2.0f * (qx * qx + qz * qz), 2.0f * (qy * qz - qw * qx),
+        2.0f * (qx * qz - qw * qy),        2.0f * (qy * qz + qw * qx),        1.0f - 2.0f * (qx * qx + qy * qy),
+    };
+    float sg[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        sg[r * 3 + 0] = R[r * 3 + 0] * sx;
+        sg[r * 3 + 1] = R[r * 3 + 1] * sy;
+        sg[r * 3 + 2] = R[r * 3 + 2] * sz;
+    }
+    auto cov = [&](int r, int c) {
+        return (sg[r * 3 + 0] * sg[c * 3 + 0] + sg[r * 3 + 1] * sg[c * 3 + 1]) + sg[r * 3 + 2] * sg[c * 3 + 2];
+    };
+    a.posop[i] = make_float4(g[0], g[1], g[2], g[3]);
+    a.cov_a[i] = make_float4(cov(0, 0), cov(0, 1), cov(0, 2), cov(1, 1));
+    a.cov_b[i] = make_float2(cov(1, 2), cov(2, 2));
+
+    // SH: reference layout is DC rgb then 15 R, 15 G, 15 B (splat/common.slang:25-31);
+    // internal layout is coefficient-major rgb triplets so that degree d touches the first
+    // ceil(3*(d+1)^2/4) planes only.
+    const float* sh = g + 12;
+#pragma unroll
+    for (uint32_t p = 0; p < SH_PLANES; ++p) {
+        float v[4];
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            const uint32_t f = p * 4 + q, k = f / 3, c = f % 3;
+            v[q] = (k == 0) ? sh[c] : sh[3 + c * 15 + (k - 1)];
+        }
+        a.sh[(size_t)p * a.n + i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+cudaError_t launch_compile_scene(const CompileLaunch& a, cudaStream_t s) {
+    if (a.n == 0) return cudaSuccess;
+    compile_scene_kernel<<<(a.n + COMPILE_THREADS - 1) / COMPILE_THREADS, COMPILE_THREADS, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-frame setup: mul(V, M), mul(P, M) per entity (splat/common.slang:102,106), camera position,
+// focal length in pixels. Row-major, every dot product accumulated left to right.
+// ---------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void mat4_mul(const float* a, const float* b, float* r) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            r[i * 4 + j] = ((a[i * 4 + 0] * b[0 * 4 + j] + a[i * 4 + 1] * b[1 * 4 + j]) + a[i * 4 + 2] * b[2 * 4 + j]) +
+                           a[i * 4 + 3] * b[3 * 4 + j];
+}
+
+__global__ void setup_kernel(PreprocessLaunch a, const __grid_constant__ CameraUbo ubo) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    const float* V = ubo.f;
+    const float* P = ubo.f + 16;
+    if (e < a.scene.entity_count) {
+        float m[16], v[16], p[16], r[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { m[k] = a.models[e * 16 + k]; v[k] = V[k]; p[k] = P[k]; }
+        mat4_mul(v, m, r);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a.vm[e * 16 + k] = r[k];
+        mat4_mul(p, m, r);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a.pm[e * 16 + k] = r[k];
+    }
+    if (e == 0) {
+        for (int k = 0; k < 16; ++k) a.cam->V[k] = V[k];
+        for (int i = 0; i < 3; ++i)
+            a.cam->cam_pos[i] = -((V[0 * 4 + i] * V[0 * 4 + 3] + V[1 * 4 + i] * V[1 * 4 + 3]) + V[2 * 4 + i] * V[2 * 4 + 3]);
+        a.cam->focal[0] = 0.5f * (float)a.width * ubo.f[32];
+        a.cam->focal[1] = 0.5f * (float)a.height * ubo.f[33];
+    }
+}
+
+cudaError_t launch_setup(const PreprocessLaunch& a, const CameraUbo& ubo, cudaStream_t s) {
+    const uint32_t threads = 64;
+    setup_kernel<<<(a.scene.entity_count + threads - 1) / threads, threads, 0, s>>>(a, ubo);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// spherical harmonics (splat/common.slang:35-80), colour is tolerance-checked only
+// ---------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float3 eval_sh(const float* shf, float x, float y, float z, int degree) {
+    constexpr float C0 = 0.28209479177387814f;
+    constexpr float C1 = 0.4886025119029199f;
+    constexpr float C2[5] = { 1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                              0.5462742152960396f };
+    constexpr float C3[7] = { -0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                              -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f };
+    float out[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        auto F = [&](int k) { return shf[3 * k + c]; };
+        float result = C0 * F(0);
+        if (degree > 0) {
+            result = ((result - C1 * y * F(1)) + C1 * z * F(2)) - C1 * x * F(3);
+            if (degree > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, zx = z * x;
+                result = ((((result + C2[0] * xy * F(4)) + C2[1] * yz * F(5)) + C2[2] * (2.0f * zz - xx - yy) * F(6)) +
+                          C2[3] * zx * F(7)) +
+                         C2[4] * (xx - yy) * F(8);
+                if (degree > 2) {
+                    // term 12 is "C3[3]*z*(2zz-3xx-3yy) + feature" in the reference (splat/common.slang:69)
+                    result = (((((((result + C3[0] * y * (3.0f * xx - yy) * F(9)) + C3[1] * xy * z * F(10)) +
+                                  C3[2] * y * (4.0f * zz - xx - yy) * F(11)) +
+                                 C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy)) +
+                                F(12)) +
+                               C3[4] * x * (4.0f * zz - xx - yy) * F(13)) +
+                              C3[5] * z * (xx - yy) * F(14)) +
+                             C3[6] * x * (xx - 3.0f * yy) * F(15);
+                }
+            }
+        }
+        result += 0.5f;
+        out[c] = fmaxf(result, 0.0f);
+    }
+    return make_float3(out[0], out[1], out[2]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused preprocess kernel
+// ---------------------------------------------------------------------------------------------------
+
+// Scan descriptor: [63:62] state | [61:32] visible-Gaussian count | [31:0] pair count.
+__device__ __forceinline__ uint64_t desc_pack(uint32_t flag, uint32_t visible, uint32_t pairs) {
+    return ((uint64_t)flag << 62) | ((uint64_t)visible << 32) | (uint64_t)pairs;
+}
+constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1ull;
+
+template <int DEG>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunch a) {
+    __shared__ uint32_t s_part;
+    __shared__ uint64_t s_base;                 // exclusive (visible, pairs) prefix of this partition
+    __shared__ float s_vm[16], s_pm[16];
+    __shared__ uint32_t s_off[PRE_THREADS];     // exclusive pair offsets inside the partition
+    __shared__ uint32_t s_xy[PRE_THREADS];      // rect origin: x0 | y0 << 16
+    __shared__ uint32_t s_w[PRE_THREADS];       // rect width
+    __shared__ uint32_t s_depth[PRE_THREADS];   // float bits of viewZ
+    __shared__ uint64_t s_warp_tot[PRE_THREADS / 32];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_part = atomicAdd(&a.ctl->scan_ticket, 1u);
+    const bool single_entity = a.scene.entity == nullptr;
+    if (single_entity && tid < 32) {
+        if (tid < 16) s_vm[tid] = a.vm[tid];
+        else s_pm[tid - 16] = a.pm[tid - 16];
+    }
+    __syncthreads();
+    const uint32_t part = s_part;
+    const uint32_t n = a.scene.n;
+    const uint32_t i = part * PRE_THREADS + tid;
+    const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX, gy = (a.height + TILE_PX - 1) / TILE_PX;
+
+    uint32_t count = 0, rect_xy = 0, rect_w = 0, depth_bits = 0;
+
+    if (i < n) {
+        const float4 po = __ldg(a.scene.posop + i);
+        const float* VM = s_vm;
+        const float* PM = s_pm;
+        float vm_l[16], pm_l[16];
+        if (!single_entity) {
+            const uint32_t e = __ldg(a.scene.entity + i);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { vm_l[k] = __ldg(a.vm + e * 16 + k); pm_l[k] = __ldg(a.pm + e * 16 + k); }
+            VM = vm_l;
+            PM = pm_l;
+        }
+        // splat/common.slang:98-119 passFrustumClipping
+        auto row_point = [&](const float* m, int r) {
+            return ((m[r * 4 + 0] * po.x + m[r * 4 + 1] * po.y) + m[r * 4 + 2] * po.z) + m[r * 4 + 3];
+        };
+        const float vx = row_point(VM, 0), vy = row_point(VM, 1), vz = row_point(VM, 2);
+        bool ok = !(vz <= 0.0f);
+        const float cx4 = row_point(PM, 0), cy4 = row_point(PM, 1), cz4 = row_point(PM, 2), cw4 = row_point(PM, 3);
+        ok = ok && !(cx4 < -1.3f * cw4 || cx4 > 1.3f * cw4);
+        ok = ok && !(cy4 < -1.3f * cw4 || cy4 > 1.3f * cw4);
+        ok = ok && !(cz4 < 0.0f || cz4 > cw4);
+        if (ok) {
+            const float inv_w = 1.0f / cw4;
+            const float proj_x = cx4 * inv_w, proj_y = cy4 * inv_w;
+
+            const float4 ca = __ldg(a.scene.cov_a + i);
+            const float2 cb = __ldg(a.scene.cov_b + i);
+            const float cov3[9] = { ca.x, ca.y, ca.z, ca.y, ca.w, cb.x, ca.z, cb.x, cb.y };
+            const float* V = a.cam->V;
+
+            // splat/volume.slang:44-63
+            const float focal_x = a.cam->focal[0], focal_y = a.cam->focal[1];
+            const float fx = focal_x / vz, fy = focal_y / vz;
+            const float tx = vx / vz, ty = vy / vz;
+            const float j02 = -fx * tx, j12 = -fy * ty;
+            float T[6];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                T[0 * 3 + j] = fx * V[0 * 4 + j] + j02 * V[2 * 4 + j];
+                T[1 * 3 + j] = fy * V[1 * 4 + j] + j12 * V[2 * 4 + j];
+            }
+            float M[6];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    M[r * 2 + j] = (cov3[r * 3 + 0] * T[j * 3 + 0] + cov3[r * 3 + 1] * T[j * 3 + 1]) + cov3[r * 3 + 2] * T[j * 3 + 2];
+            const float c00 = (T[0] * M[0] + T[1] * M[2]) + T[2] * M[4];
+            const float c10 = (T[3] * M[0] + T[4] * M[2]) + T[5] * M[4];
+            const float c11 = (T[3] * M[1] + T[4] * M[3]) + T[5] * M[5];
+
+            // project.slang:60-72
+            const float cvx = c00 + 0.3f, cvy = c10, cvz = c11 + 0.3f;
+            const float det = cvx * cvz - cvy * cvy;
+            if (det != 0.0f) {
+                const float det_inv = 1.0f / det;
+                const float mid = 0.5f * (cvx + cvz);
+                const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+                const float lambda_1 = mid + sq, lambda_2 = mid - sq;
+                const float radius = ceilf(3.0f * sqrtf(fmaxf(lambda_1, lambda_2)));
+                if (fabsf(radius) <= 3.402823466e+38f) {
+                    // splat/volume.slang:3-17
+                    const float px = ((proj_x + 1.0f) * (float)a.width - 1.0f) * 0.5f;
+                    const float py = ((proj_y + 1.0f) * (float)a.height - 1.0f) * 0.5f;
+                    const int x0 = min((int)gx, max(0, __float2int_rz((px - radius) / 16.0f)));
+                    const int y0 = min((int)gy, max(0, __float2int_rz((py - radius) / 16.0f)));
+                    const int x1 = min((int)gx, max(0, __float2int_rz((((px + radius) + 16.0f) - 1.0f) / 16.0f)));
+                    const int y1 = min((int)gy, max(0, __float2int_rz((((py + radius) + 16.0f) - 1.0f) / 16.0f)));
+                    count = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+                    if (count != 0) {
+                        rect_xy = (uint32_t)x0 | ((uint32_t)y0 << 16);
+                        rect_w = (uint32_t)(x1 - x0);
+                        depth_bits = __float_as_uint(vz);
+
+                        // colour (project.slang:82-83)
+                        float shf[48];
+                        constexpr int PLANES = DEG == 0 ? 1 : DEG == 1 ? 3 : DEG == 2 ? 7 : 12;
+#pragma unroll
+                        for (int p = 0; p < PLANES; ++p) {
+                            const float4 v = __ldg(a.scene.sh + (size_t)p * n + i);
+                            shf[4 * p + 0] = v.x; shf[4 * p + 1] = v.y; shf[4 * p + 2] = v.z; shf[4 * p + 3] = v.w;
+                        }
+                        float dx = po.x - a.cam->cam_pos[0], dy = po.y - a.cam->cam_pos[1], dz = po.z - a.cam->cam_pos[2];
+                        const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
+                        dx /= len; dy /= len; dz /= len;
+                        const float3 col = eval_sh(shf, dx, dy, dz, DEG);
+
+                        float4* rec = reinterpret_cast<float4*>(a.recs + i);
+                        rec[0] = make_float4(px, py, cvz * det_inv, -cvy * det_inv);
+                        rec[1] = make_float4(cvx * det_inv, po.w, vz, radius);
+                        rec[2] = make_float4(col.x, col.y, col.z, 0.0f);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- partition-local exclusive scan of (visible, pairs) -----------------------------------------
+    const uint64_t mine = ((uint64_t)(count != 0) << 32) | count;
+    uint64_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += up;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    s_xy[tid] = rect_xy;
+    s_w[tid] = rect_w;
+    s_depth[tid] = depth_bits;
+    __syncthreads();
+    uint64_t warp_excl = 0, total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < PRE_THREADS / 32; ++w) {
+        const uint64_t t = s_warp_tot[w];
+        if (w < warp) warp_excl += t;
+        total += t;
+    }
+    const uint32_t local_excl = (uint32_t)(warp_excl + incl - mine);
+    s_off[tid] = local_excl;
+
+    // ---- decoupled look-back across partitions (warp 0) ---------------------------------------------
+    const uint32_t num_parts = (n + PRE_THREADS - 1) / PRE_THREADS;
+    if (warp == 0) {
+        uint64_t exclusive = 0;
+        if (part == 0) {
+            if (lane == 0) st_relaxed_u64(a.scan_desc, ((uint64_t)FLAG_PREFIX << 62) | total);
+        } else {
+            if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_AGGREGATE << 62) | total);
+            int look = (int)part - 1;
+            while (true) {
+                const int idx = look - (int)lane;
+                uint64_t d = ((uint64_t)FLAG_PREFIX << 62);  // virtual partition -1: inclusive prefix 0
+                if (idx >= 0) {
+                    do { d = ld_relaxed_u64(a.scan_desc + idx); } while ((d >> 62) == FLAG_INVALID);
+                }
+                const uint32_t prefix_mask = __ballot_sync(0xffffffffu, (d >> 62) == FLAG_PREFIX);
+                const uint32_t first = prefix_mask ? (uint32_t)__ffs((int)prefix_mask) - 1u : 32u;
+                uint64_t v = (lane <= first) ? (d & DESC_VALUE_MASK) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                exclusive += v;
+                if (prefix_mask) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_PREFIX << 62) | (exclusive + total));
+        }
+        if (lane == 0) {
+            s_base = exclusive;
+            if (part == num_parts - 1) {
+                const uint64_t all = exclusive + total;
+                a.ctl->pairs_total = (uint32_t)all;
+                a.ctl->visible = (uint32_t)(all >> 32);
+                a.offsets[n] = (uint32_t)all;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t base = (uint32_t)s_base;
+    if (i < n) a.offsets[i] = base + local_excl;
+
+    // ---- duplication: the partition's pairs are emitted cooperatively, coalesced ---------------------
+    const uint32_t part_pairs = (uint32_t)total;
+    for (uint32_t j = tid; j < part_pairs; j += PRE_THREADS) {
+        uint32_t g = 0;
+#pragma unroll
+        for (uint32_t step = PRE_THREADS / 2; step >= 1; step >>= 1)
+            if (s_off[g + step] <= j) g += step;
+        const uint32_t r = j - s_off[g];
+        const uint32_t w = s_w[g], xy = s_xy[g];
+        const uint32_t ry = r / w, rx = r - ry * w;
+        const uint32_t tile = ((xy >> 16) + ry) * gx + ((xy & 0xffffu) + rx);
+        const uint32_t out = base + j;
+        if (out < a.capacity) {
+            a.keys[out] = ((uint64_t)tile << 32) | s_depth[g];
+            a.vals[out] = part * PRE_THREADS + g;
+        }
+    }
+}
+
+cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s) {
+    if (a.scene.n == 0) return cudaSuccess;
+    const uint32_t grid = (a.scene.n + PRE_THREADS - 1) / PRE_THREADS;
+    switch (a.sh_degree) {
+        case 0: preprocess_kernel<0><<<grid, PRE_THREADS, 0, s>>>(a); break;
+        case 1: preprocess_kernel<1><<<grid, PRE_THREADS, 0, s>>>(a); break;
+        case 2: preprocess_kernel<2><<<grid, PRE_THREADS, 0, s>>>(a); break;
+        default: preprocess_kernel<3><<<grid, PRE_THREADS, 0, s>>>(a); break;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// introspection: internal records -> reference Splat layout (splat.slang:33-39)
+// ---------------------------------------------------------------------------------------------------
+
+__global__ void export_splats_kernel(const SplatRec* recs, const uint32_t* offsets, uint32_t n, uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t off = offsets[i], cnt = offsets[i + 1] - off;
+    uint32_t* o = out + (size_t)i * 12;
+    if (cnt == 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) o[k] = 0;
+        o[3] = off;
+        return;
+    }
+    const SplatRec r = recs[i];
+    o[0] = __float_as_uint(r.r); o[1] = __float_as_uint(r.g); o[2] = __float_as_uint(r.b); o[3] = off;
+    o[4] = __float_as_uint(r.px); o[5] = __float_as_uint(r.py); o[6] = __float_as_uint(r.view_z); o[7] = __float_as_uint(r.radius);
+    o[8] = __float_as_uint(r.conic_a); o[9] = __float_as_uint(r.conic_b); o[10] = __float_as_uint(r.conic_c);
+    o[11] = __float_as_uint(r.opacity);
+}
+
+cudaError_t launch_export_splats(const SplatRec* recs, const uint32_t* offsets, uint32_t n, void* out48, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    export_splats_kernel<<<(n + 255) / 256, 256, 0, s>>>(recs, offsets, n, reinterpret_cast<uint32_t*>(out48));
+    return cudaGetLastError();
+}
+
+}  // namespace tpdcu

@@ -1,0 +1,294 @@
+// sort.cu — stable 64-bit-key / 32-bit-value LSD radix sort in the onesweep style
+// (one up-front multi-digit histogram, then ONE read + ONE write of every pair per 8-bit digit,
+// with a chained decoupled look-back across tiles instead of a separate scan per pass).
+//
+// Replaces the reference's 4-way radix sorter: radix-shuffle.slang:37-150, radix-prefixA.slang:37-169,
+// radix-prefixB.slang:37-168, radix-mapping.slang:38-116 driven by GaussianEngine.cpp:822-841
+// (23 passes x 4 dispatches at 1080p, ~1.1 KB of DRAM traffic per pair) with
+// ceil(end_bit/8) passes (6 at 1080p) of 24 B per pair each, + 8 B per pair for the histogram.
+//
+// The number of pairs lives in device memory (FrameCtl::pairs_total): the host never learns P inside a
+// frame, grids are sized by the buffer capacity and surplus CTAs exit on their ticket.
+#include "common.cuh"
+
+namespace tpdcu {
+
+constexpr uint32_t HIST_THREADS = 512;
+constexpr uint32_t HIST_KPT = 8;
+constexpr uint32_t LOOKBACK_VALUE_MASK = (1u << 30) - 1u;
+
+__device__ __forceinline__ uint32_t digit_of(uint64_t key, uint32_t shift, uint32_t mask) {
+    return (uint32_t)(key >> shift) & mask;
+}
+__host__ __device__ __forceinline__ uint32_t pass_mask(uint32_t pass, uint32_t end_bit) {
+    const uint32_t left = end_bit - pass * SORT_RADIX_BITS;
+    return left >= SORT_RADIX_BITS ? (SORT_BINS - 1u) : ((1u << left) - 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// up-front histogram of every digit (one read of the keys)
+// ---------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t* __restrict__ keys, FrameCtl* ctl,
+                                                                  uint32_t n_host, uint32_t capacity, uint32_t num_passes,
+                                                                  uint32_t end_bit) {
+    __shared__ uint32_t h[SORT_MAX_PASSES][SORT_BINS];
+    const uint32_t n = n_host == UINT32_MAX ? min(ctl->pairs_total, capacity) : n_host;
+    for (uint32_t k = threadIdx.x; k < num_passes * SORT_BINS; k += HIST_THREADS) (&h[0][0])[k] = 0;
+    __syncthreads();
+    const uint32_t chunk = HIST_THREADS * HIST_KPT;
+    for (uint32_t base = blockIdx.x * chunk; base < n; base += gridDim.x * chunk) {
+        uint64_t k[HIST_KPT];
+#pragma unroll
+        for (uint32_t j = 0; j < HIST_KPT; ++j) {
+            const uint32_t idx = base + j * HIST_THREADS + threadIdx.x;
+            k[j] = idx < n ? __ldg(keys + idx) : 0ull;
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < HIST_KPT; ++j) {
+            const uint32_t idx = base + j * HIST_THREADS + threadIdx.x;
+            if (idx < n) {
+                for (uint32_t p = 0; p < num_passes; ++p)
+                    atomicAdd(&h[p][digit_of(k[j], p * SORT_RADIX_BITS, pass_mask(p, end_bit))], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < num_passes * SORT_BINS; k += HIST_THREADS) {
+        const uint32_t c = (&h[0][0])[k];
+        if (c) atomicAdd(&ctl->hist[0][0] + k, c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// plan: exclusive digit offsets, identity-pass detection, ping-pong schedule
+// ---------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, SortPlan* plan, uint32_t n_host, uint32_t capacity,
+                                                               uint32_t num_passes) {
+    __shared__ uint32_t s_warp[SORT_BINS / 32];
+    __shared__ uint32_t s_skip[SORT_MAX_PASSES];
+    const uint32_t n = n_host == UINT32_MAX ? min(ctl->pairs_total, capacity) : n_host;
+    const uint32_t b = threadIdx.x, lane = b & 31u, warp = b >> 5;
+    if (b < SORT_MAX_PASSES) s_skip[b] = 0;
+    __syncthreads();
+    for (uint32_t p = 0; p < num_passes; ++p) {
+        const uint32_t c = ctl->hist[p][b];
+        if (c == n) s_skip[p] = 1;  // every key falls in this bin (also true for n == 0)
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wex = 0;
+        for (uint32_t w = 0; w < warp; ++w) wex += s_warp[w];
+        ctl->hist[p][b] = wex + incl - c;
+        __syncthreads();
+    }
+    if (b == 0) {
+        uint32_t sel = 0, run = 0;
+        for (uint32_t p = 0; p < SORT_MAX_PASSES; ++p) {
+            const uint32_t skip = p < num_passes ? s_skip[p] : 1u;
+            plan->skip[p] = skip;
+            plan->src_sel[p] = sel;
+            if (!skip) { sel ^= 1u; ++run; }
+        }
+        plan->n = n;
+        plan->num_passes = num_passes;
+        plan->final_sel = sel;
+        plan->passes_run = run;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// one onesweep pass
+// ---------------------------------------------------------------------------------------------------
+
+struct OnesweepSmem {
+    uint64_t keys[SORT_TILE];
+    uint32_t vals[SORT_TILE];
+    uint32_t warp_hist[SORT_WARPS][SORT_BINS];
+    uint32_t global_base[SORT_BINS];
+    uint32_t scan[SORT_BINS / 32];
+    uint32_t part;
+};
+
+__global__ void __launch_bounds__(SORT_THREADS, 2)
+onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, FrameCtl* ctl,
+                const SortPlan* __restrict__ plan, uint32_t* lookback_pass, uint32_t pass, uint32_t end_bit) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
+
+    if (plan->skip[pass]) return;
+    const uint32_t n = plan->n;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) sm.part = atomicAdd(&ctl->sort_ticket[pass], 1u);
+    // zero the per-warp histograms while the ticket is in flight
+    for (uint32_t k = tid; k < SORT_WARPS * SORT_BINS; k += SORT_THREADS) (&sm.warp_hist[0][0])[k] = 0;
+    __syncthreads();
+    const uint32_t part = sm.part;
+    const uint64_t tile_base64 = (uint64_t)part * SORT_TILE;
+    if (tile_base64 >= n) return;
+    const uint32_t tile_base = (uint32_t)tile_base64;
+    const uint32_t n_valid = min(SORT_TILE, n - tile_base);
+
+    const uint32_t src = plan->src_sel[pass];
+    const uint64_t* __restrict__ src_keys = src ? keys1 : keys0;
+    const uint32_t* __restrict__ src_vals = src ? vals1 : vals0;
+    uint64_t* __restrict__ dst_keys = src ? keys0 : keys1;
+    uint32_t* __restrict__ dst_vals = src ? vals0 : vals1;
+    const uint32_t shift = pass * SORT_RADIX_BITS, mask = pass_mask(pass, end_bit);
+
+    // ---- load (warp-striped: item k of lane l sits at warp_base + 32k + l) --------------------------
+    uint64_t key[SORT_KPT];
+    uint32_t val[SORT_KPT];
+    const uint32_t warp_base = tile_base + warp * (32u * SORT_KPT);
+#pragma unroll
+    for (uint32_t k = 0; k < SORT_KPT; ++k) {
+        const uint32_t idx = warp_base + k * 32u + lane;
+        key[k] = idx < n ? src_keys[idx] : ~0ull;  // padding sorts last inside the tile
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < SORT_KPT; ++k) {
+        const uint32_t idx = warp_base + k * 32u + lane;
+        val[k] = idx < n ? src_vals[idx] : 0u;
+    }
+
+    // ---- early counts: per-warp digit histograms ----------------------------------------------------
+#pragma unroll
+    for (uint32_t k = 0; k < SORT_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_of(key[k], shift, mask)], 1u);
+    __syncthreads();
+
+    // ---- per-bin: exclusive prefix over warps, tile count, publish the aggregate ---------------------
+    uint32_t bin_count = 0, bin_count_valid = 0, bin_base = 0;
+    uint32_t* lb = lookback_pass + (size_t)part * SORT_BINS;
+    if (tid < SORT_BINS) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < SORT_WARPS; ++w) {
+            const uint32_t c = sm.warp_hist[w][tid];
+            sm.warp_hist[w][tid] = sum;
+            sum += c;
+        }
+        bin_count = sum;
+        bin_count_valid = (tid == mask) ? sum - (SORT_TILE - n_valid) : sum;  // padding lives in the top bin
+        st_relaxed_u32(lb + tid, ((part == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) << 30) | bin_count_valid);
+        // exclusive scan of the tile's bin counts -> first local rank of every bin
+        uint32_t incl = bin_count;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += up;
+        }
+        if (lane == 31) sm.scan[warp] = incl;
+        bin_base = incl - bin_count;
+    }
+    __syncthreads();
+    if (tid < SORT_BINS) {
+        for (uint32_t w = 0; w < warp; ++w) bin_base += sm.scan[w];
+#pragma unroll
+        for (uint32_t w = 0; w < SORT_WARPS; ++w) sm.warp_hist[w][tid] += bin_base;
+    }
+    __syncthreads();
+
+    // ---- stable ranking: peers with the same digit inside a 32-key row, rows in order ----------------
+    uint32_t rank[SORT_KPT];
+#pragma unroll
+    for (uint32_t k = 0; k < SORT_KPT; ++k) {
+        const uint32_t d = digit_of(key[k], shift, mask);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t lower = __popc(peers & lanemask_lt());
+        const uint32_t base = sm.warp_hist[warp][d];
+        __syncwarp();
+        if (lower == 0) sm.warp_hist[warp][d] = base + __popc(peers);
+        __syncwarp();
+        rank[k] = base + lower;
+    }
+
+    // ---- decoupled look-back, one thread per bin -----------------------------------------------------
+    if (tid < SORT_BINS) {
+        uint32_t excl = 0;
+        if (part > 0) {
+            const uint32_t* p = lookback_pass + (size_t)(part - 1) * SORT_BINS + tid;
+            while (true) {
+                uint32_t v;
+                do { v = ld_relaxed_u32(p); } while ((v >> 30) == FLAG_INVALID);
+                excl += v & LOOKBACK_VALUE_MASK;
+                if ((v >> 30) == FLAG_PREFIX) break;
+                p -= SORT_BINS;
+            }
+            st_relaxed_u32(lb + tid, (FLAG_PREFIX << 30) | (excl + bin_count_valid));
+        }
+        sm.global_base[tid] = ctl->hist[pass][tid] + excl - bin_base;
+    }
+
+    // ---- scatter through shared memory so that global stores are contiguous per bin ------------------
+#pragma unroll
+    for (uint32_t k = 0; k < SORT_KPT; ++k) {
+        sm.keys[rank[k]] = key[k];
+        sm.vals[rank[k]] = val[k];
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n_valid; i += SORT_THREADS) {
+        const uint64_t kk = sm.keys[i];
+        const uint32_t pos = sm.global_base[digit_of(kk, shift, mask)] + i;
+        dst_keys[pos] = kk;
+        dst_vals[pos] = sm.vals[i];
+    }
+}
+
+__global__ void sort_copy_result_kernel(const uint64_t* keys1, const uint32_t* vals1, uint64_t* out_keys, uint32_t* out_vals,
+                                        const uint64_t* keys0, const uint32_t* vals0, const SortPlan* plan) {
+    const uint64_t* sk = plan->final_sel ? keys1 : keys0;
+    const uint32_t* sv = plan->final_sel ? vals1 : vals0;
+    const uint32_t n = plan->n;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        out_keys[i] = sk[i];
+        out_vals[i] = sv[i];
+    }
+}
+
+uint32_t sort_parts(uint32_t capacity) { return (capacity + SORT_TILE - 1) / SORT_TILE; }
+
+cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cudaEvent_t ev_after_plan) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OnesweepSmem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const uint32_t num_passes = (a.end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
+    const uint32_t bound = n_host == UINT32_MAX ? a.capacity : n_host;
+    if (bound == 0 || num_passes == 0) {
+        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host == UINT32_MAX ? UINT32_MAX : 0u, a.capacity, 0);
+        if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
+        return cudaGetLastError();
+    }
+    const uint32_t chunk = HIST_THREADS * HIST_KPT;
+    uint32_t hist_grid = (bound + chunk - 1) / chunk;
+    const uint32_t hist_max = (uint32_t)a.sm_count * 4u;
+    if (hist_grid > hist_max) hist_grid = hist_max;
+    sort_hist_kernel<<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.ctl, n_host, a.capacity, num_passes, a.end_bit);
+    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host, a.capacity, num_passes);
+    if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
+    const uint32_t parts = sort_parts(bound);
+    const uint32_t parts_cap = sort_parts(a.capacity);
+    for (uint32_t p = 0; p < num_passes; ++p) {
+        onesweep_kernel<<<parts, SORT_THREADS, sizeof(OnesweepSmem), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan,
+                                                                          a.lookback + (size_t)p * parts_cap * SORT_BINS, p, a.end_bit);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sort_copy_result(const SortLaunch& a, uint64_t* out_keys, uint32_t* out_vals, uint32_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    uint32_t grid = (n + 255) / 256;
+    if (grid > (uint32_t)a.sm_count * 8u) grid = (uint32_t)a.sm_count * 8u;
+    sort_copy_result_kernel<<<grid, 256, 0, s>>>(a.keys[1], a.vals[1], out_keys, out_vals, a.keys[0], a.vals[0], a.plan);
+    return cudaGetLastError();
+}
+
+}  // namespace tpdcu
