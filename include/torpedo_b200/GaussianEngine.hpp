@@ -69,6 +69,19 @@ public:
         _compiled = true;
     }
 
+    /// compile() for a cloud that already sits in THIS GPU's memory as 240-byte records (e.g. after the NCCL broadcast
+    /// that replicates a scene across the GPUs of a box): one group entity, slot 0.
+    Entity compileDevice(const void* deviceRecords240, uint32_t gaussianCount, const Settings& settings = Settings::getDefault(),
+                         void* stream = nullptr) {
+        if (gaussianCount == 0) return Entity{ 0 };
+        _shDegree = settings.sphericalHarmonicsDegree > 3 ? 3 : settings.sphericalHarmonicsDegree;
+        check(tpdcu_upload_gaussians_device(_ctx, deviceRecords240, gaussianCount, nullptr, 1, stream), "tpdcu_upload_gaussians_device");
+        const Entity cloud{ 0 };
+        _transformHost->update(std::map<Entity, uint32_t>{ { cloud, 0u } });
+        _compiled = true;
+        return cloud;
+    }
+
     [[nodiscard]] const std::unique_ptr<TransformHost>& getTransformHost() const noexcept { return _transformHost; }
 
     /// GaussianEngine::updateCameraBuffer (GaussianEngine.cpp:764-775): view | proj*view | (P00, P11).

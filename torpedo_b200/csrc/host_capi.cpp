@@ -86,6 +86,9 @@ void tpdh_engine_destroy(tpd::GaussianEngine* e) { delete e; }
 int tpdh_engine_compile(tpd::GaussianEngine* e, const tpd::Scene* s, uint32_t shDegree) {
     return guarded([&] { e->compile(*s, tpd::GaussianEngine::Settings{ shDegree }); });
 }
+int tpdh_engine_compile_device(tpd::GaussianEngine* e, const void* dRecs240, uint32_t count, uint32_t shDegree, void* stream) {
+    return guarded([&] { e->compileDevice(dRecs240, count, tpd::GaussianEngine::Settings{ shDegree }, stream); });
+}
 int tpdh_engine_transform(tpd::GaussianEngine* e, uint32_t entity, const float m[16]) {
     return guarded([&] {
         tpd::mat4 t;

@@ -46,6 +46,7 @@ TPDH_SYMBOLS = {
     "tpdh_engine_create": (vp, [u32, u32, i32]),
     "tpdh_engine_destroy": (None, [vp]),
     "tpdh_engine_compile": (i32, [vp, vp, u32]),
+    "tpdh_engine_compile_device": (i32, [vp, vp, u32, u32, vp]),
     "tpdh_engine_transform": (i32, [vp, u32, vp]),
     "tpdh_engine_raster_frame": (i32, [vp, vp, vp]),
     "tpdh_engine_draw": (i32, [vp, vp, sz]),
@@ -202,6 +203,11 @@ class GaussianEngine:
     def compile(self, scene: Scene, settings: Settings | None = None) -> None:
         settings = settings or Settings()
         _hcheck(tpdhost().tpdh_engine_compile(self._h, scene._h, settings.spherical_harmonics_degree))
+
+    def compile_device(self, d_records240: int, count: int, settings: Settings | None = None, stream: int | None = None) -> None:
+        """compile() for a cloud already resident on this GPU as 240-byte records (after the NCCL scene broadcast)."""
+        settings = settings or Settings()
+        _hcheck(tpdhost().tpdh_engine_compile_device(self._h, d_records240, count, settings.spherical_harmonics_degree, stream))
 
     def transform(self, entity: int, matrix) -> None:
         """engine->getTransformHost()->transform(entity, mat4) (rendering/src/TransformHost.cpp:3-11)"""

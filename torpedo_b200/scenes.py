@@ -13,6 +13,9 @@ SH layout: sh[0:3] = DC rgb, then 15 R, 15 G, 15 B coefficients (splat/common.sl
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 GAUSSIAN_FLOATS = 60
@@ -118,22 +121,46 @@ def garden(n: int, seed: int, log_scale_mean: float = -5.1, log_scale_std: float
     log-normal-like scales; random rotations; opacity = sigmoid(N(0.5, 2)); DC colour U(0,1); small non-zero higher-order
     SH so that degree 3 and the band-3 quirk (splat/common.slang:69) are exercised."""
     g = np.zeros((n, GAUSSIAN_FLOATS), dtype=np.float32)
-    dirs = _unit_dirs(seed, 10, n)
-    in_ball = uniform(seed, 1, n) < 0.7
-    r_ball = 1.5 * np.maximum(np.maximum(uniform(seed, 2, n), uniform(seed, 3, n)), uniform(seed, 4, n))  # pdf ~ r^2
-    r_shell = 3.0 + 9.0 * uniform(seed, 5, n)
-    r = np.where(in_ball, r_ball, r_shell)
-    g[:, 0:3] = (dirs * r[:, None]).astype(np.float32)
-    g[:, 3] = sigmoid_det(0.5 + 2.0 * normalish(seed, 20, n)).astype(np.float32)
-    g[:, 4:8] = _unit_quats(seed, 30, n).astype(np.float32)
-    for k in range(3):
+
+    def positions():
+        dirs = _unit_dirs(seed, 10, n)
+        in_ball = uniform(seed, 1, n) < 0.7
+        r_ball = 1.5 * np.maximum(np.maximum(uniform(seed, 2, n), uniform(seed, 3, n)), uniform(seed, 4, n))  # pdf ~ r^2
+        r_shell = 3.0 + 9.0 * uniform(seed, 5, n)
+        r = np.where(in_ball, r_ball, r_shell)
+        g[:, 0:3] = (dirs * r[:, None]).astype(np.float32)
+
+    def opacity():
+        g[:, 3] = sigmoid_det(0.5 + 2.0 * normalish(seed, 20, n)).astype(np.float32)
+
+    def quats():
+        g[:, 4:8] = _unit_quats(seed, 30, n).astype(np.float32)
+
+    def scale(k):
         g[:, 8 + k] = exp_det(log_scale_mean + log_scale_std * normalish(seed, 40 + k, n)).astype(np.float32)
-    g[:, 11] = 1.0
-    for k in range(3):
+
+    def dc(k):
         g[:, 12 + k] = rgb2sh(uniform(seed, 50 + k, n))
-    for k in range(45):
+
+    def rest(k):
         g[:, 15 + k] = (sh_rest_std * normalish(seed, 60 + k, n)).astype(np.float32)
+
+    jobs = [positions, opacity, quats] + [lambda k=k: scale(k) for k in range(3)] + [lambda k=k: dc(k) for k in range(3)] + \
+           [lambda k=k: rest(k) for k in range(45)]
+    g[:, 11] = 1.0
+    _run_jobs(jobs, n)
     return g
+
+
+def _run_jobs(jobs, n):
+    """Columns are independent and numpy releases the GIL: fill them in parallel for multi-million-point scenes."""
+    if n < 200_000:
+        for j in jobs:
+            j()
+        return
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+        for f in [pool.submit(j) for j in jobs]:
+            f.result()
 
 
 def dense_volume(n: int, seed: int = 4, log_scale_mean: float = -4.8, log_scale_std: float = 0.6) -> np.ndarray:
