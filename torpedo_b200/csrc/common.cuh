@@ -12,8 +12,8 @@ constexpr uint32_t SH_PLANES = 12;        // 48 SH floats as 12 float4 planes
 constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
-constexpr uint32_t SORT_THREADS = 512;
-constexpr uint32_t SORT_KPT = 8;          // keys per thread
+constexpr uint32_t SORT_THREADS = 256;
+constexpr uint32_t SORT_KPT = 16;         // keys per thread
 constexpr uint32_t SORT_TILE = SORT_THREADS * SORT_KPT;
 constexpr uint32_t SORT_WARPS = SORT_THREADS / 32;
 
@@ -45,14 +45,21 @@ struct FrameCam {
     float pad[3];
 };
 
-// Internal splat record (48 B): the reference's Splat (splat.slang:33-39) permuted so that the
-// blend stage's always-needed 6 floats come first.
-struct __align__(16) SplatRec {
-    float px, py, conic_a, conic_b;       // float4 #0
-    float conic_c, opacity, view_z, radius; // float4 #1
-    float r, g, b, pad;                   // float4 #2
+// Internal per-Gaussian outputs of the preprocess stage (the reference's 48-byte Splat, splat.slang:33-39, re-cut by
+// consumer): `SplatGeo` is everything the blend stage needs to decide whether a pixel is touched (one 32-byte sector per
+// gather), `color` is only fetched for splats that survive the per-tile cull, `depth_radius` is introspection-only.
+struct __align__(32) SplatGeo {
+    float px, py, conic_a, conic_b;         // float4 #0
+    float conic_c, opacity, ext_x, ext_y;   // float4 #1: ext = half-extents of the alpha >= 1/255 region (conservative)
 };
-static_assert(sizeof(SplatRec) == 48, "SplatRec must be 48 bytes");
+static_assert(sizeof(SplatGeo) == 32, "SplatGeo must be one 32-byte sector");
+
+struct SplatArrays {
+    SplatGeo* geo;                        // written for visible Gaussians only
+    float4* color;                        // rgb (+pad), written for visible Gaussians only
+    float2* depth_radius;                 // (viewZ, radius), visible only; read by tpdcu_read_splats
+    uint32_t* offsets;                    // exclusive pair offset per Gaussian, n + 1 entries (prefix.slang semantics)
+};
 
 struct SceneArrays {
     const float4* posop;                  // xyz + opacity
@@ -103,8 +110,7 @@ struct PreprocessLaunch {
     float* pm;                            // device scratch, entity_count x 16
     FrameCtl* ctl;
     uint64_t* scan_desc;                  // zeroed, one per partition
-    SplatRec* recs;
-    uint32_t* offsets;                    // exclusive pair offset per Gaussian (n + 1 entries)
+    SplatArrays out;
     uint64_t* keys;
     uint32_t* vals;
     uint32_t capacity;
@@ -112,7 +118,8 @@ struct PreprocessLaunch {
 };
 struct CameraUbo { float f[34]; };          // the reference's 136-byte Camera block, passed by value
 cudaError_t launch_setup(const PreprocessLaunch& a, const CameraUbo& ubo, cudaStream_t s);
-cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s);
+cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s);   // geometry + scan + duplication
+cudaError_t launch_color(const PreprocessLaunch& a, cudaStream_t s);        // SH colour of the visible Gaussians
 
 struct CompileLaunch {
     const float* recs240;                 // device, n x 60 floats
@@ -143,7 +150,8 @@ struct RasterLaunch {
     const uint64_t* keys[2];
     const uint32_t* vals[2];
     const SortPlan* plan;
-    const SplatRec* recs;
+    const SplatGeo* geo;
+    const float4* color;
     uint32_t* ranges;                     // zeroed, tiles x 2
     uint8_t* out;
     size_t pitch;
@@ -155,6 +163,6 @@ cudaError_t launch_blend(const RasterLaunch& a, cudaStream_t s);
 
 cudaError_t launch_sort_copy_result(const SortLaunch& a, uint64_t* out_keys, uint32_t* out_vals, uint32_t n, cudaStream_t s);
 
-cudaError_t launch_export_splats(const SplatRec* recs, const uint32_t* offsets, uint32_t n, void* out48, cudaStream_t s);
+cudaError_t launch_export_splats(const SplatArrays& a, uint32_t n, void* out48, cudaStream_t s);
 
 }  // namespace tpdcu

@@ -161,7 +161,7 @@ __device__ __forceinline__ float3 eval_sh(const float* shf, float x, float y, fl
 }
 
 // ---------------------------------------------------------------------------------------------------
-// fused preprocess kernel
+// fused geometry + scan + duplication kernel (no colour: see color_kernel below)
 // ---------------------------------------------------------------------------------------------------
 
 // Scan descriptor: [63:62] state | [61:32] visible-Gaussian count | [31:0] pair count.
@@ -170,11 +170,10 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t flag, uint32_t visible, u
 }
 constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1ull;
 
-template <int DEG>
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunch a) {
     __shared__ uint32_t s_part;
     __shared__ uint64_t s_base;                 // exclusive (visible, pairs) prefix of this partition
-    __shared__ float s_vm[16], s_pm[16];
+    __shared__ float s_vm[16], s_pm[16], s_v[12], s_focal[2];
     __shared__ uint32_t s_off[PRE_THREADS];     // exclusive pair offsets inside the partition
     __shared__ uint32_t s_xy[PRE_THREADS];      // rect origin: x0 | y0 << 16
     __shared__ uint32_t s_w[PRE_THREADS];       // rect width
@@ -184,9 +183,10 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunc
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_part = atomicAdd(&a.ctl->scan_ticket, 1u);
     const bool single_entity = a.scene.entity == nullptr;
-    if (single_entity && tid < 32) {
-        if (tid < 16) s_vm[tid] = a.vm[tid];
-        else s_pm[tid - 16] = a.pm[tid - 16];
+    if (tid < 16) {
+        if (single_entity) { s_vm[tid] = a.vm[tid]; s_pm[tid] = a.pm[tid]; }
+        if (tid < 12) s_v[tid] = a.cam->V[tid];
+        if (tid < 2) s_focal[tid] = a.cam->focal[tid];
     }
     __syncthreads();
     const uint32_t part = s_part;
@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunc
 
     if (i < n) {
         const float4 po = __ldg(a.scene.posop + i);
+        const float4 ca = __ldg(a.scene.cov_a + i);   // issued before the cull: one round trip instead of two
+        const float2 cb = __ldg(a.scene.cov_b + i);
         const float* VM = s_vm;
         const float* PM = s_pm;
         float vm_l[16], pm_l[16];
@@ -221,15 +223,11 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunc
         if (ok) {
             const float inv_w = 1.0f / cw4;
             const float proj_x = cx4 * inv_w, proj_y = cy4 * inv_w;
-
-            const float4 ca = __ldg(a.scene.cov_a + i);
-            const float2 cb = __ldg(a.scene.cov_b + i);
             const float cov3[9] = { ca.x, ca.y, ca.z, ca.y, ca.w, cb.x, ca.z, cb.x, cb.y };
-            const float* V = a.cam->V;
+            const float* V = s_v;
 
             // splat/volume.slang:44-63
-            const float focal_x = a.cam->focal[0], focal_y = a.cam->focal[1];
-            const float fx = focal_x / vz, fy = focal_y / vz;
+            const float fx = s_focal[0] / vz, fy = s_focal[1] / vz;
             const float tx = vx / vz, ty = vy / vz;
             const float j02 = -fx * tx, j12 = -fy * ty;
             float T[6];
@@ -271,23 +269,23 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunc
                         rect_w = (uint32_t)(x1 - x0);
                         depth_bits = __float_as_uint(vz);
 
-                        // colour (project.slang:82-83)
-                        float shf[48];
-                        constexpr int PLANES = DEG == 0 ? 1 : DEG == 1 ? 3 : DEG == 2 ? 7 : 12;
-#pragma unroll
-                        for (int p = 0; p < PLANES; ++p) {
-                            const float4 v = __ldg(a.scene.sh + (size_t)p * n + i);
-                            shf[4 * p + 0] = v.x; shf[4 * p + 1] = v.y; shf[4 * p + 2] = v.z; shf[4 * p + 3] = v.w;
+                        // Conservative half-extents of the region where alpha = opacity*exp(power) can reach 1/255
+                        // (blend.slang:88-89): power >= -t, t = ln(255*opacity), is the ellipse d^T conic d <= 2t whose
+                        // bounding box is sqrt(2t*cov). Used ONLY to skip splats that cannot touch a tile; margins cover fp32
+                        // rounding of power/exp in the blend. Ill-conditioned covariances are never culled.
+                        float ext_x = 3.0e38f, ext_y = 3.0e38f;
+                        const float t = logf(255.0f * po.w);
+                        if (!(t >= 0.0f)) {
+                            ext_x = ext_y = -1.0e30f;  // opacity < 1/255: alpha < 1/255 at every pixel
+                        } else if (det > 1e-3f * (cvx * cvz) && cvx > 0.0f && cvz > 0.0f) {
+                            const float tt = 2.0f * (t + 0.02f);
+                            ext_x = sqrtf(tt * cvx) * 1.0002f + 0.02f;
+                            ext_y = sqrtf(tt * cvz) * 1.0002f + 0.02f;
                         }
-                        float dx = po.x - a.cam->cam_pos[0], dy = po.y - a.cam->cam_pos[1], dz = po.z - a.cam->cam_pos[2];
-                        const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
-                        dx /= len; dy /= len; dz /= len;
-                        const float3 col = eval_sh(shf, dx, dy, dz, DEG);
-
-                        float4* rec = reinterpret_cast<float4*>(a.recs + i);
-                        rec[0] = make_float4(px, py, cvz * det_inv, -cvy * det_inv);
-                        rec[1] = make_float4(cvx * det_inv, po.w, vz, radius);
-                        rec[2] = make_float4(col.x, col.y, col.z, 0.0f);
+                        float4* geo = reinterpret_cast<float4*>(a.out.geo + i);
+                        geo[0] = make_float4(px, py, cvz * det_inv, -cvy * det_inv);
+                        geo[1] = make_float4(cvx * det_inv, po.w, ext_x, ext_y);
+                        a.out.depth_radius[i] = make_float2(vz, radius);
                     }
                 }
             }
@@ -349,13 +347,13 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunc
                 const uint64_t all = exclusive + total;
                 a.ctl->pairs_total = (uint32_t)all;
                 a.ctl->visible = (uint32_t)(all >> 32);
-                a.offsets[n] = (uint32_t)all;
+                a.out.offsets[n] = (uint32_t)all;
             }
         }
     }
     __syncthreads();
     const uint32_t base = (uint32_t)s_base;
-    if (i < n) a.offsets[i] = base + local_excl;
+    if (i < n) a.out.offsets[i] = base + local_excl;
 
     // ---- duplication: the partition's pairs are emitted cooperatively, coalesced ---------------------
     const uint32_t part_pairs = (uint32_t)total;
@@ -378,12 +376,46 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunc
 
 cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s) {
     if (a.scene.n == 0) return cudaSuccess;
-    const uint32_t grid = (a.scene.n + PRE_THREADS - 1) / PRE_THREADS;
+    preprocess_kernel<<<(a.scene.n + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// colour: SH evaluation for the visible Gaussians only (project.slang:82-83, splat/common.slang:35-80). No barriers, no
+// look-back: a pure stream of 16 B position + up to 192 B of SH in, 16 B out, runs after the geometry kernel.
+// ---------------------------------------------------------------------------------------------------
+
+constexpr uint32_t COLOR_THREADS = 256;
+
+template <int DEG>
+__global__ void __launch_bounds__(COLOR_THREADS) color_kernel(PreprocessLaunch a) {
+    const uint32_t n = a.scene.n;
+    const uint32_t i = blockIdx.x * COLOR_THREADS + threadIdx.x;
+    if (i >= n) return;
+    if (a.out.offsets[i + 1] == a.out.offsets[i]) return;  // culled: the reference leaves its colour stale
+    const float4 po = __ldg(a.scene.posop + i);
+    float shf[48];
+    constexpr int PLANES = DEG == 0 ? 1 : DEG == 1 ? 3 : DEG == 2 ? 7 : 12;
+#pragma unroll
+    for (int p = 0; p < PLANES; ++p) {
+        const float4 v = __ldg(a.scene.sh + (size_t)p * n + i);
+        shf[4 * p + 0] = v.x; shf[4 * p + 1] = v.y; shf[4 * p + 2] = v.z; shf[4 * p + 3] = v.w;
+    }
+    float dx = po.x - a.cam->cam_pos[0], dy = po.y - a.cam->cam_pos[1], dz = po.z - a.cam->cam_pos[2];
+    const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
+    dx /= len; dy /= len; dz /= len;
+    const float3 col = eval_sh(shf, dx, dy, dz, DEG);
+    a.out.color[i] = make_float4(col.x, col.y, col.z, 0.0f);
+}
+
+cudaError_t launch_color(const PreprocessLaunch& a, cudaStream_t s) {
+    if (a.scene.n == 0) return cudaSuccess;
+    const uint32_t grid = (a.scene.n + COLOR_THREADS - 1) / COLOR_THREADS;
     switch (a.sh_degree) {
-        case 0: preprocess_kernel<0><<<grid, PRE_THREADS, 0, s>>>(a); break;
-        case 1: preprocess_kernel<1><<<grid, PRE_THREADS, 0, s>>>(a); break;
-        case 2: preprocess_kernel<2><<<grid, PRE_THREADS, 0, s>>>(a); break;
-        default: preprocess_kernel<3><<<grid, PRE_THREADS, 0, s>>>(a); break;
+        case 0: color_kernel<0><<<grid, COLOR_THREADS, 0, s>>>(a); break;
+        case 1: color_kernel<1><<<grid, COLOR_THREADS, 0, s>>>(a); break;
+        case 2: color_kernel<2><<<grid, COLOR_THREADS, 0, s>>>(a); break;
+        default: color_kernel<3><<<grid, COLOR_THREADS, 0, s>>>(a); break;
     }
     return cudaGetLastError();
 }
@@ -392,10 +424,10 @@ cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s) {
 // introspection: internal records -> reference Splat layout (splat.slang:33-39)
 // ---------------------------------------------------------------------------------------------------
 
-__global__ void export_splats_kernel(const SplatRec* recs, const uint32_t* offsets, uint32_t n, uint32_t* out) {
+__global__ void export_splats_kernel(SplatArrays a, uint32_t n, uint32_t* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t off = offsets[i], cnt = offsets[i + 1] - off;
+    const uint32_t off = a.offsets[i], cnt = a.offsets[i + 1] - off;
     uint32_t* o = out + (size_t)i * 12;
     if (cnt == 0) {
 #pragma unroll
@@ -403,16 +435,18 @@ __global__ void export_splats_kernel(const SplatRec* recs, const uint32_t* offse
         o[3] = off;
         return;
     }
-    const SplatRec r = recs[i];
-    o[0] = __float_as_uint(r.r); o[1] = __float_as_uint(r.g); o[2] = __float_as_uint(r.b); o[3] = off;
-    o[4] = __float_as_uint(r.px); o[5] = __float_as_uint(r.py); o[6] = __float_as_uint(r.view_z); o[7] = __float_as_uint(r.radius);
+    const SplatGeo r = a.geo[i];
+    const float4 c = a.color[i];
+    const float2 zr = a.depth_radius[i];
+    o[0] = __float_as_uint(c.x); o[1] = __float_as_uint(c.y); o[2] = __float_as_uint(c.z); o[3] = off;
+    o[4] = __float_as_uint(r.px); o[5] = __float_as_uint(r.py); o[6] = __float_as_uint(zr.x); o[7] = __float_as_uint(zr.y);
     o[8] = __float_as_uint(r.conic_a); o[9] = __float_as_uint(r.conic_b); o[10] = __float_as_uint(r.conic_c);
     o[11] = __float_as_uint(r.opacity);
 }
 
-cudaError_t launch_export_splats(const SplatRec* recs, const uint32_t* offsets, uint32_t n, void* out48, cudaStream_t s) {
+cudaError_t launch_export_splats(const SplatArrays& a, uint32_t n, void* out48, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    export_splats_kernel<<<(n + 255) / 256, 256, 0, s>>>(recs, offsets, n, reinterpret_cast<uint32_t*>(out48));
+    export_splats_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, n, reinterpret_cast<uint32_t*>(out48));
     return cudaGetLastError();
 }
 

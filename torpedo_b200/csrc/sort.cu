@@ -16,6 +16,7 @@ namespace tpdcu {
 constexpr uint32_t HIST_THREADS = 512;
 constexpr uint32_t HIST_KPT = 8;
 constexpr uint32_t LOOKBACK_VALUE_MASK = (1u << 30) - 1u;
+constexpr uint32_t LOOKBACK_BATCH = 8;
 
 __device__ __forceinline__ uint32_t digit_of(uint64_t key, uint32_t shift, uint32_t mask) {
     return (uint32_t)(key >> shift) & mask;
@@ -115,8 +116,12 @@ struct OnesweepSmem {
     uint32_t scan[SORT_BINS / 32];
     uint32_t part;
 };
+static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phases");
 
-__global__ void __launch_bounds__(SORT_THREADS, 2)
+// One CTA = one tile of SORT_TILE pairs. Phases (6 block barriers):
+//   ticket + zero per-warp histograms | load keys (+values), early counts | per-bin: warp prefix, publish aggregate, bin scan |
+//   stable ranking (match.any) + key scatter to smem | look-back per bin | coalesced key write-out, value scatter | value write-out
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, FrameCtl* ctl,
                 const SortPlan* __restrict__ plan, uint32_t* lookback_pass, uint32_t pass, uint32_t end_bit) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -126,8 +131,11 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     const uint32_t n = plan->n;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) sm.part = atomicAdd(&ctl->sort_ticket[pass], 1u);
-    // zero the per-warp histograms while the ticket is in flight
-    for (uint32_t k = tid; k < SORT_WARPS * SORT_BINS; k += SORT_THREADS) (&sm.warp_hist[0][0])[k] = 0;
+    {
+        uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[0][0]);
+#pragma unroll
+        for (uint32_t k = 0; k < SORT_WARPS * SORT_BINS / 4 / SORT_THREADS; ++k) z[tid + k * SORT_THREADS] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     const uint32_t part = sm.part;
     const uint64_t tile_base64 = (uint64_t)part * SORT_TILE;
@@ -144,17 +152,13 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
 
     // ---- load (warp-striped: item k of lane l sits at warp_base + 32k + l) --------------------------
     uint64_t key[SORT_KPT];
-    uint32_t val[SORT_KPT];
-    const uint32_t warp_base = tile_base + warp * (32u * SORT_KPT);
+    const uint32_t warp_base = tile_base + warp * (32u * SORT_KPT) + lane;
+    if (n_valid == SORT_TILE) {
 #pragma unroll
-    for (uint32_t k = 0; k < SORT_KPT; ++k) {
-        const uint32_t idx = warp_base + k * 32u + lane;
-        key[k] = idx < n ? src_keys[idx] : ~0ull;  // padding sorts last inside the tile
-    }
+        for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = src_keys[warp_base + k * 32u];
+    } else {
 #pragma unroll
-    for (uint32_t k = 0; k < SORT_KPT; ++k) {
-        const uint32_t idx = warp_base + k * 32u + lane;
-        val[k] = idx < n ? src_vals[idx] : 0u;
+        for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = (warp_base + k * 32u) < n ? src_keys[warp_base + k * 32u] : ~0ull;  // padding sorts last
     }
 
     // ---- early counts: per-warp digit histograms ----------------------------------------------------
@@ -162,39 +166,34 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     for (uint32_t k = 0; k < SORT_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_of(key[k], shift, mask)], 1u);
     __syncthreads();
 
-    // ---- per-bin: exclusive prefix over warps, tile count, publish the aggregate ---------------------
-    uint32_t bin_count = 0, bin_count_valid = 0, bin_base = 0;
+    // ---- per-bin (thread == bin): exclusive prefix over warps, publish the tile aggregate, scan the bins -------------
     uint32_t* lb = lookback_pass + (size_t)part * SORT_BINS;
-    if (tid < SORT_BINS) {
-        uint32_t sum = 0;
+    uint32_t bin_count = 0;
 #pragma unroll
-        for (uint32_t w = 0; w < SORT_WARPS; ++w) {
-            const uint32_t c = sm.warp_hist[w][tid];
-            sm.warp_hist[w][tid] = sum;
-            sum += c;
-        }
-        bin_count = sum;
-        bin_count_valid = (tid == mask) ? sum - (SORT_TILE - n_valid) : sum;  // padding lives in the top bin
-        st_relaxed_u32(lb + tid, ((part == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) << 30) | bin_count_valid);
-        // exclusive scan of the tile's bin counts -> first local rank of every bin
-        uint32_t incl = bin_count;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl += up;
-        }
-        if (lane == 31) sm.scan[warp] = incl;
-        bin_base = incl - bin_count;
+    for (uint32_t w = 0; w < SORT_WARPS; ++w) {
+        const uint32_t c = sm.warp_hist[w][tid];
+        sm.warp_hist[w][tid] = bin_count;
+        bin_count += c;
     }
+    const uint32_t bin_count_valid = (tid == mask) ? bin_count - (SORT_TILE - n_valid) : bin_count;  // padding lives in the top bin
+    st_relaxed_u32(lb + tid, ((part == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) << 30) | bin_count_valid);
+    uint32_t incl = bin_count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += up;
+    }
+    if (lane == 31) sm.scan[warp] = incl;
+    uint32_t bin_base = incl - bin_count;
     __syncthreads();
-    if (tid < SORT_BINS) {
-        for (uint32_t w = 0; w < warp; ++w) bin_base += sm.scan[w];
 #pragma unroll
-        for (uint32_t w = 0; w < SORT_WARPS; ++w) sm.warp_hist[w][tid] += bin_base;
-    }
+    for (uint32_t w = 0; w < SORT_BINS / 32; ++w)
+        if (w < warp) bin_base += sm.scan[w];
+#pragma unroll
+    for (uint32_t w = 0; w < SORT_WARPS; ++w) sm.warp_hist[w][tid] += bin_base;
     __syncthreads();
 
-    // ---- stable ranking: peers with the same digit inside a 32-key row, rows in order ----------------
+    // ---- stable ranking: peers with the same digit inside a 32-key row, rows in order; keys go straight to smem ------
     uint32_t rank[SORT_KPT];
 #pragma unroll
     for (uint32_t k = 0; k < SORT_KPT; ++k) {
@@ -206,37 +205,67 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         if (lower == 0) sm.warp_hist[warp][d] = base + __popc(peers);
         __syncwarp();
         rank[k] = base + lower;
+        sm.keys[rank[k]] = key[k];
+    }
+
+    // values: issue the loads now, their latency hides behind the look-back
+    uint32_t val[SORT_KPT];
+    if (n_valid == SORT_TILE) {
+#pragma unroll
+        for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = src_vals[warp_base + k * 32u];
+    } else {
+#pragma unroll
+        for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = (warp_base + k * 32u) < n ? src_vals[warp_base + k * 32u] : 0u;
     }
 
     // ---- decoupled look-back, one thread per bin -----------------------------------------------------
-    if (tid < SORT_BINS) {
+    {
         uint32_t excl = 0;
         if (part > 0) {
-            const uint32_t* p = lookback_pass + (size_t)(part - 1) * SORT_BINS + tid;
-            while (true) {
-                uint32_t v;
-                do { v = ld_relaxed_u32(p); } while ((v >> 30) == FLAG_INVALID);
-                excl += v & LOOKBACK_VALUE_MASK;
-                if ((v >> 30) == FLAG_PREFIX) break;
-                p -= SORT_BINS;
+            // Tiles in flight publish their aggregate long before their prefix, so the walk back to the nearest PREFIX can
+            // be hundreds of tiles deep right after launch: read LOOKBACK_BATCH descriptors per round trip, consume in order.
+            int look = (int)part - 1;
+            bool done = false;
+            while (!done) {
+                uint32_t v[LOOKBACK_BATCH];
+#pragma unroll
+                for (int j = 0; j < (int)LOOKBACK_BATCH; ++j)
+                    v[j] = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
+#pragma unroll
+                for (int j = 0; j < (int)LOOKBACK_BATCH; ++j) {
+                    if (!done) {
+                        uint32_t x = v[j];
+                        while ((x >> 30) == FLAG_INVALID) x = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
+                        excl += x & LOOKBACK_VALUE_MASK;
+                        done = (x >> 30) == FLAG_PREFIX;  // tile 0 always carries a PREFIX, so look - j never goes below 0 unconsumed
+                    }
+                }
+                look -= (int)LOOKBACK_BATCH;
             }
             st_relaxed_u32(lb + tid, (FLAG_PREFIX << 30) | (excl + bin_count_valid));
         }
         sm.global_base[tid] = ctl->hist[pass][tid] + excl - bin_base;
     }
+    __syncthreads();
 
-    // ---- scatter through shared memory so that global stores are contiguous per bin ------------------
+    // ---- write-out: position i of the locally sorted tile goes to global_base[digit] + i (contiguous per bin) ---------
+    uint32_t pos[SORT_KPT];
 #pragma unroll
     for (uint32_t k = 0; k < SORT_KPT; ++k) {
-        sm.keys[rank[k]] = key[k];
-        sm.vals[rank[k]] = val[k];
+        const uint32_t i = tid + k * SORT_THREADS;
+        if (i < n_valid) {
+            const uint64_t kk = sm.keys[i];
+            pos[k] = sm.global_base[digit_of(kk, shift, mask)] + i;
+            dst_keys[pos[k]] = kk;
+        }
     }
+#pragma unroll
+    for (uint32_t k = 0; k < SORT_KPT; ++k) sm.vals[rank[k]] = val[k];
     __syncthreads();
-    for (uint32_t i = tid; i < n_valid; i += SORT_THREADS) {
-        const uint64_t kk = sm.keys[i];
-        const uint32_t pos = sm.global_base[digit_of(kk, shift, mask)] + i;
-        dst_keys[pos] = kk;
-        dst_vals[pos] = sm.vals[i];
+#pragma unroll
+    for (uint32_t k = 0; k < SORT_KPT; ++k) {
+        const uint32_t i = tid + k * SORT_THREADS;
+        if (i < n_valid) dst_vals[pos[k]] = sm.vals[i];
     }
 }
 

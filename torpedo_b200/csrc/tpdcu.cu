@@ -54,7 +54,9 @@ struct tpdcu_ctx {
     float2* cov_b = nullptr;
     float4* sh = nullptr;
     uint32_t* entity = nullptr;
-    SplatRec* recs = nullptr;
+    SplatGeo* geo = nullptr;
+    float4* color = nullptr;
+    float2* depth_radius = nullptr;
     uint32_t* offsets = nullptr;
     float* models = nullptr;
     float* vm = nullptr;
@@ -120,8 +122,8 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static void free_scene(tpdcu_ctx* c) {
     cudaFree(c->posop); cudaFree(c->cov_a); cudaFree(c->cov_b); cudaFree(c->sh); cudaFree(c->entity);
-    cudaFree(c->recs); cudaFree(c->offsets); cudaFree(c->models); cudaFree(c->vm); cudaFree(c->pm);
-    c->posop = c->cov_a = nullptr; c->cov_b = nullptr; c->sh = nullptr; c->entity = nullptr; c->recs = nullptr;
+    cudaFree(c->geo); cudaFree(c->color); cudaFree(c->depth_radius); cudaFree(c->offsets); cudaFree(c->models); cudaFree(c->vm); cudaFree(c->pm);
+    c->posop = c->cov_a = nullptr; c->cov_b = nullptr; c->sh = nullptr; c->entity = nullptr; c->geo = nullptr; c->color = nullptr; c->depth_radius = nullptr;
     c->offsets = nullptr; c->models = c->vm = c->pm = nullptr;
     c->n = 0; c->entity_count = 0;
 }
@@ -204,7 +206,7 @@ static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cud
     p.models = c->models; p.cam = c->cam; p.vm = c->vm; p.pm = c->pm;
     p.ctl = ctl;
     p.scan_desc = reinterpret_cast<uint64_t*>(c->zero_region + c->off_scan_desc);
-    p.recs = c->recs; p.offsets = c->offsets;
+    p.out = SplatArrays{ c->geo, c->color, c->depth_radius, c->offsets };
     p.keys = c->keys[0]; p.vals = c->vals[0];
     p.capacity = c->capacity;
     p.width = c->width; p.height = c->height; p.sh_degree = std::min(sh_degree, 3u);  // GaussianEngine.cpp:366-370
@@ -213,6 +215,7 @@ static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cud
     CK(launch_setup(p, cu, s));
     if (t) CK(cudaEventRecord(c->ev[1], s));
     CK(launch_preprocess(p, s));
+    CK(launch_color(p, s));
     if (c->keep_unsorted && c->capacity) {
         if (c->unsorted_capacity < c->capacity) {
             cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
@@ -236,7 +239,7 @@ static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cud
 
     RasterLaunch ra{};
     ra.keys[0] = c->keys[0]; ra.keys[1] = c->keys[1]; ra.vals[0] = c->vals[0]; ra.vals[1] = c->vals[1];
-    ra.plan = c->plan; ra.recs = c->recs;
+    ra.plan = c->plan; ra.geo = c->geo; ra.color = c->color;
     ra.ranges = reinterpret_cast<uint32_t*>(c->zero_region + c->off_ranges);
     ra.out = out; ra.pitch = pitch; ra.capacity = c->capacity; ra.width = c->width; ra.height = c->height;
     CK(launch_ranges(ra, s));
@@ -365,7 +368,9 @@ static int upload_common(tpdcu_ctx* c, const void* d_recs, uint32_t n, const uin
     CK(cudaMalloc(&c->cov_a, (size_t)n * sizeof(float4)));
     CK(cudaMalloc(&c->cov_b, (size_t)n * sizeof(float2)));
     CK(cudaMalloc(&c->sh, (size_t)n * SH_PLANES * sizeof(float4)));
-    CK(cudaMalloc(&c->recs, (size_t)n * sizeof(SplatRec)));
+    CK(cudaMalloc(&c->geo, (size_t)n * sizeof(SplatGeo)));
+    CK(cudaMalloc(&c->color, (size_t)n * sizeof(float4)));
+    CK(cudaMalloc(&c->depth_radius, (size_t)n * sizeof(float2)));
     CK(cudaMalloc(&c->offsets, ((size_t)n + 1) * sizeof(uint32_t)));
     CK(cudaMalloc(&c->models, (size_t)entity_count * 16 * sizeof(float)));
     CK(cudaMalloc(&c->vm, (size_t)entity_count * 16 * sizeof(float)));
@@ -381,7 +386,6 @@ static int upload_common(tpdcu_ctx* c, const void* d_recs, uint32_t n, const uin
     for (uint32_t e = 0; e < entity_count; ++e)
         for (int k = 0; k < 4; ++k) c->models_host[(size_t)e * 16 + k * 5] = 1.0f;
     c->models_dirty = true;
-    CK(cudaMemsetAsync(c->recs, 0, (size_t)n * sizeof(SplatRec), s));
     CompileLaunch cl{ reinterpret_cast<const float*>(d_recs), c->posop, c->cov_a, c->cov_b, c->sh, n };
     CK(launch_compile_scene(cl, s));
     return TPDCU_OK;
@@ -583,7 +587,7 @@ int tpdcu_read_splats(tpdcu_ctx* c, void* host_splats48, uint32_t n) {
     if (n == 0) return TPDCU_OK;
     void* tmp = nullptr;
     CK(cudaMalloc(&tmp, (size_t)n * TPDCU_SPLAT_BYTES));
-    cudaError_t e = launch_export_splats(c->recs, c->offsets, n, tmp, c->last_stream);
+    cudaError_t e = launch_export_splats(SplatArrays{ c->geo, c->color, c->depth_radius, c->offsets }, n, tmp, c->last_stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_splats48, tmp, (size_t)n * TPDCU_SPLAT_BYTES, cudaMemcpyDeviceToHost, c->last_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->last_stream);
     cudaFree(tmp);
