@@ -7,7 +7,9 @@
 namespace tpdcu {
 
 constexpr uint32_t TILE_PX = 16;          // BLOCK_X == BLOCK_Y (reference GaussianEngine.h:122-123)
-constexpr uint32_t PRE_THREADS = 256;     // Gaussians per preprocess partition (one per thread)
+constexpr uint32_t PRE_THREADS = 256;
+constexpr uint32_t PRE_ITEMS = 4;         // Gaussians per thread
+constexpr uint32_t PRE_PART = PRE_THREADS * PRE_ITEMS;  // Gaussians per preprocess partition (one look-back each)
 constexpr uint32_t SH_PLANES = 12;        // 48 SH floats as 12 float4 planes
 constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
@@ -22,7 +24,9 @@ struct FrameCtl {
     uint32_t scan_ticket;                 // preprocess partition tickets
     uint32_t pairs_total;                 // P (tilesRendered), may exceed capacity
     uint32_t visible;                     // Gaussians with tiles > 0
-    uint32_t pad0;
+    uint32_t depth_max;                   // max float bits of viewZ over the visible Gaussians (atomicMax)
+    uint32_t inv_depth_min;               // ~min float bits (atomicMax on the complement, so zero-init works)
+    uint32_t pad0[3];
     uint32_t sort_ticket[SORT_MAX_PASSES];
     uint32_t hist[SORT_MAX_PASSES][SORT_BINS];  // global digit histograms (then exclusive offsets)
 };
@@ -33,6 +37,10 @@ struct SortPlan {
     uint32_t num_passes;
     uint32_t final_sel;                   // which ping-pong buffer holds the result
     uint32_t passes_run;
+    uint32_t bias;                        // subtracted from the low (depth) word of every key before digit extraction
+    uint32_t depth_bits;                  // significant bits of (depth - bias); the tile id is packed right above them
+    uint32_t total_bits;                  // depth_bits + tile bits: what the passes actually sort on
+    uint32_t pad;
     uint32_t skip[SORT_MAX_PASSES];       // pass is an identity permutation (single occupied bin)
     uint32_t src_sel[SORT_MAX_PASSES];    // ping-pong buffer the pass reads from
 };
@@ -138,7 +146,7 @@ struct SortLaunch {
     SortPlan* plan;
     uint32_t* lookback;                   // zeroed, [num_passes][parts_cap][SORT_BINS]
     uint32_t capacity;                    // launch bound for grids
-    uint32_t end_bit;
+    uint32_t end_bit;                     // 32 + tile bits (frame path) or the caller's end bit (standalone)
     int sm_count;
 };
 // n is taken from ctl->pairs_total clamped to capacity (frame path) when n_host == UINT32_MAX,

@@ -170,15 +170,103 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t flag, uint32_t visible, u
 }
 constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1ull;
 
+struct Projected {
+    uint32_t count, rect_xy, rect_w, depth_bits;
+};
+
+// project.slang:33-90 for one Gaussian (colour excluded). Writes SplatGeo / depth_radius when visible.
+__device__ __forceinline__ Projected project_one(const PreprocessLaunch& a, uint32_t i, const float4 po, const float4 ca, const float2 cb,
+                                                 const float* VM, const float* PM, const float* V, const float* focal, uint32_t gx,
+                                                 uint32_t gy) {
+    Projected out{ 0u, 0u, 0u, 0u };
+    // splat/common.slang:98-119 passFrustumClipping
+    auto row_point = [&](const float* m, int r) {
+        return ((m[r * 4 + 0] * po.x + m[r * 4 + 1] * po.y) + m[r * 4 + 2] * po.z) + m[r * 4 + 3];
+    };
+    const float vx = row_point(VM, 0), vy = row_point(VM, 1), vz = row_point(VM, 2);
+    if (vz <= 0.0f) return out;
+    const float cx4 = row_point(PM, 0), cy4 = row_point(PM, 1), cz4 = row_point(PM, 2), cw4 = row_point(PM, 3);
+    if (cx4 < -1.3f * cw4 || cx4 > 1.3f * cw4) return out;
+    if (cy4 < -1.3f * cw4 || cy4 > 1.3f * cw4) return out;
+    if (cz4 < 0.0f || cz4 > cw4) return out;
+    const float inv_w = 1.0f / cw4;
+    const float proj_x = cx4 * inv_w, proj_y = cy4 * inv_w;
+    const float cov3[9] = { ca.x, ca.y, ca.z, ca.y, ca.w, cb.x, ca.z, cb.x, cb.y };
+
+    // splat/volume.slang:44-63
+    const float fx = focal[0] / vz, fy = focal[1] / vz;
+    const float tx = vx / vz, ty = vy / vz;
+    const float j02 = -fx * tx, j12 = -fy * ty;
+    float T[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        T[0 * 3 + j] = fx * V[0 * 4 + j] + j02 * V[2 * 4 + j];
+        T[1 * 3 + j] = fy * V[1 * 4 + j] + j12 * V[2 * 4 + j];
+    }
+    float M[6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            M[r * 2 + j] = (cov3[r * 3 + 0] * T[j * 3 + 0] + cov3[r * 3 + 1] * T[j * 3 + 1]) + cov3[r * 3 + 2] * T[j * 3 + 2];
+    const float c00 = (T[0] * M[0] + T[1] * M[2]) + T[2] * M[4];
+    const float c10 = (T[3] * M[0] + T[4] * M[2]) + T[5] * M[4];
+    const float c11 = (T[3] * M[1] + T[4] * M[3]) + T[5] * M[5];
+
+    // project.slang:60-72
+    const float cvx = c00 + 0.3f, cvy = c10, cvz = c11 + 0.3f;
+    const float det = cvx * cvz - cvy * cvy;
+    if (det == 0.0f) return out;
+    const float det_inv = 1.0f / det;
+    const float mid = 0.5f * (cvx + cvz);
+    const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
+    const float lambda_1 = mid + sq, lambda_2 = mid - sq;
+    const float radius = ceilf(3.0f * sqrtf(fmaxf(lambda_1, lambda_2)));
+    if (!(fabsf(radius) <= 3.402823466e+38f)) return out;  // canonical: a non-finite radius is culled
+
+    // splat/volume.slang:3-17
+    const float px = ((proj_x + 1.0f) * (float)a.width - 1.0f) * 0.5f;
+    const float py = ((proj_y + 1.0f) * (float)a.height - 1.0f) * 0.5f;
+    const int x0 = min((int)gx, max(0, __float2int_rz((px - radius) / 16.0f)));
+    const int y0 = min((int)gy, max(0, __float2int_rz((py - radius) / 16.0f)));
+    const int x1 = min((int)gx, max(0, __float2int_rz((((px + radius) + 16.0f) - 1.0f) / 16.0f)));
+    const int y1 = min((int)gy, max(0, __float2int_rz((((py + radius) + 16.0f) - 1.0f) / 16.0f)));
+    out.count = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+    if (out.count == 0) return out;
+    out.rect_xy = (uint32_t)x0 | ((uint32_t)y0 << 16);
+    out.rect_w = (uint32_t)(x1 - x0);
+    out.depth_bits = __float_as_uint(vz);
+
+    // Conservative half-extents of the region where alpha = opacity*exp(power) can reach 1/255 (blend.slang:88-89):
+    // power >= -t, t = ln(255*opacity), is the ellipse d^T conic d <= 2t whose bounding box is sqrt(2t*cov). Used ONLY to
+    // skip splats that cannot touch a tile; the margins cover fp32 rounding of power/exp in the blend. Ill-conditioned
+    // covariances are never culled.
+    float ext_x = 3.0e38f, ext_y = 3.0e38f;
+    const float t = logf(255.0f * po.w);
+    if (!(t >= 0.0f)) {
+        ext_x = ext_y = -1.0e30f;  // opacity < 1/255: alpha < 1/255 at every pixel
+    } else if (det > 1e-3f * (cvx * cvz) && cvx > 0.0f && cvz > 0.0f) {
+        const float tt = 2.0f * (t + 0.02f);
+        ext_x = sqrtf(tt * cvx) * 1.0002f + 0.02f;
+        ext_y = sqrtf(tt * cvz) * 1.0002f + 0.02f;
+    }
+    float4* geo = reinterpret_cast<float4*>(a.out.geo + i);
+    geo[0] = make_float4(px, py, cvz * det_inv, -cvy * det_inv);
+    geo[1] = make_float4(cvx * det_inv, po.w, ext_x, ext_y);
+    a.out.depth_radius[i] = make_float2(vz, radius);
+    return out;
+}
+
+// One CTA = one partition of PRE_PART consecutive Gaussians (PRE_ITEMS per thread, striped so that loads coalesce).
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunch a) {
     __shared__ uint32_t s_part;
     __shared__ uint64_t s_base;                 // exclusive (visible, pairs) prefix of this partition
     __shared__ float s_vm[16], s_pm[16], s_v[12], s_focal[2];
-    __shared__ uint32_t s_off[PRE_THREADS];     // exclusive pair offsets inside the partition
-    __shared__ uint32_t s_xy[PRE_THREADS];      // rect origin: x0 | y0 << 16
-    __shared__ uint32_t s_w[PRE_THREADS];       // rect width
-    __shared__ uint32_t s_depth[PRE_THREADS];   // float bits of viewZ
-    __shared__ uint64_t s_warp_tot[PRE_THREADS / 32];
+    __shared__ uint32_t s_off[PRE_PART];        // exclusive pair offsets inside the partition
+    __shared__ uint32_t s_xy[PRE_PART];         // rect origin: x0 | y0 << 16
+    __shared__ uint32_t s_w[PRE_PART];          // rect width
+    __shared__ uint32_t s_depth[PRE_PART];      // float bits of viewZ
+    __shared__ uint64_t s_warp_tot[PRE_ITEMS][PRE_THREADS / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_part = atomicAdd(&a.ctl->scan_ticket, 1u);
@@ -191,132 +279,89 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunc
     __syncthreads();
     const uint32_t part = s_part;
     const uint32_t n = a.scene.n;
-    const uint32_t i = part * PRE_THREADS + tid;
+    const uint32_t first = part * PRE_PART + tid;
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX, gy = (a.height + TILE_PX - 1) / TILE_PX;
 
-    uint32_t count = 0, rect_xy = 0, rect_w = 0, depth_bits = 0;
-
-    if (i < n) {
-        const float4 po = __ldg(a.scene.posop + i);
-        const float4 ca = __ldg(a.scene.cov_a + i);   // issued before the cull: one round trip instead of two
-        const float2 cb = __ldg(a.scene.cov_b + i);
-        const float* VM = s_vm;
-        const float* PM = s_pm;
-        float vm_l[16], pm_l[16];
-        if (!single_entity) {
-            const uint32_t e = __ldg(a.scene.entity + i);
+    // ---- geometry: all loads first, then the arithmetic ---------------------------------------------------------------
+    float4 po[PRE_ITEMS], ca[PRE_ITEMS];
+    float2 cb[PRE_ITEMS];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) { vm_l[k] = __ldg(a.vm + e * 16 + k); pm_l[k] = __ldg(a.pm + e * 16 + k); }
-            VM = vm_l;
-            PM = pm_l;
+    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
+        const uint32_t i = first + k * PRE_THREADS;
+        if (i < n) {
+            po[k] = __ldg(a.scene.posop + i);
+            ca[k] = __ldg(a.scene.cov_a + i);
+            cb[k] = __ldg(a.scene.cov_b + i);
         }
-        // splat/common.slang:98-119 passFrustumClipping
-        auto row_point = [&](const float* m, int r) {
-            return ((m[r * 4 + 0] * po.x + m[r * 4 + 1] * po.y) + m[r * 4 + 2] * po.z) + m[r * 4 + 3];
-        };
-        const float vx = row_point(VM, 0), vy = row_point(VM, 1), vz = row_point(VM, 2);
-        bool ok = !(vz <= 0.0f);
-        const float cx4 = row_point(PM, 0), cy4 = row_point(PM, 1), cz4 = row_point(PM, 2), cw4 = row_point(PM, 3);
-        ok = ok && !(cx4 < -1.3f * cw4 || cx4 > 1.3f * cw4);
-        ok = ok && !(cy4 < -1.3f * cw4 || cy4 > 1.3f * cw4);
-        ok = ok && !(cz4 < 0.0f || cz4 > cw4);
-        if (ok) {
-            const float inv_w = 1.0f / cw4;
-            const float proj_x = cx4 * inv_w, proj_y = cy4 * inv_w;
-            const float cov3[9] = { ca.x, ca.y, ca.z, ca.y, ca.w, cb.x, ca.z, cb.x, cb.y };
-            const float* V = s_v;
-
-            // splat/volume.slang:44-63
-            const float fx = s_focal[0] / vz, fy = s_focal[1] / vz;
-            const float tx = vx / vz, ty = vy / vz;
-            const float j02 = -fx * tx, j12 = -fy * ty;
-            float T[6];
+    }
+    Projected pr[PRE_ITEMS];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                T[0 * 3 + j] = fx * V[0 * 4 + j] + j02 * V[2 * 4 + j];
-                T[1 * 3 + j] = fy * V[1 * 4 + j] + j12 * V[2 * 4 + j];
-            }
-            float M[6];
+    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
+        const uint32_t i = first + k * PRE_THREADS;
+        pr[k] = Projected{ 0u, 0u, 0u, 0u };
+        if (i < n) {
+            if (single_entity) {
+                pr[k] = project_one(a, i, po[k], ca[k], cb[k], s_vm, s_pm, s_v, s_focal, gx, gy);
+            } else {
+                float vm_l[16], pm_l[16];
+                const uint32_t e = __ldg(a.scene.entity + i);
 #pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    M[r * 2 + j] = (cov3[r * 3 + 0] * T[j * 3 + 0] + cov3[r * 3 + 1] * T[j * 3 + 1]) + cov3[r * 3 + 2] * T[j * 3 + 2];
-            const float c00 = (T[0] * M[0] + T[1] * M[2]) + T[2] * M[4];
-            const float c10 = (T[3] * M[0] + T[4] * M[2]) + T[5] * M[4];
-            const float c11 = (T[3] * M[1] + T[4] * M[3]) + T[5] * M[5];
-
-            // project.slang:60-72
-            const float cvx = c00 + 0.3f, cvy = c10, cvz = c11 + 0.3f;
-            const float det = cvx * cvz - cvy * cvy;
-            if (det != 0.0f) {
-                const float det_inv = 1.0f / det;
-                const float mid = 0.5f * (cvx + cvz);
-                const float sq = sqrtf(fmaxf(0.1f, mid * mid - det));
-                const float lambda_1 = mid + sq, lambda_2 = mid - sq;
-                const float radius = ceilf(3.0f * sqrtf(fmaxf(lambda_1, lambda_2)));
-                if (fabsf(radius) <= 3.402823466e+38f) {
-                    // splat/volume.slang:3-17
-                    const float px = ((proj_x + 1.0f) * (float)a.width - 1.0f) * 0.5f;
-                    const float py = ((proj_y + 1.0f) * (float)a.height - 1.0f) * 0.5f;
-                    const int x0 = min((int)gx, max(0, __float2int_rz((px - radius) / 16.0f)));
-                    const int y0 = min((int)gy, max(0, __float2int_rz((py - radius) / 16.0f)));
-                    const int x1 = min((int)gx, max(0, __float2int_rz((((px + radius) + 16.0f) - 1.0f) / 16.0f)));
-                    const int y1 = min((int)gy, max(0, __float2int_rz((((py + radius) + 16.0f) - 1.0f) / 16.0f)));
-                    count = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
-                    if (count != 0) {
-                        rect_xy = (uint32_t)x0 | ((uint32_t)y0 << 16);
-                        rect_w = (uint32_t)(x1 - x0);
-                        depth_bits = __float_as_uint(vz);
-
-                        // Conservative half-extents of the region where alpha = opacity*exp(power) can reach 1/255
-                        // (blend.slang:88-89): power >= -t, t = ln(255*opacity), is the ellipse d^T conic d <= 2t whose
-                        // bounding box is sqrt(2t*cov). Used ONLY to skip splats that cannot touch a tile; margins cover fp32
-                        // rounding of power/exp in the blend. Ill-conditioned covariances are never culled.
-                        float ext_x = 3.0e38f, ext_y = 3.0e38f;
-                        const float t = logf(255.0f * po.w);
-                        if (!(t >= 0.0f)) {
-                            ext_x = ext_y = -1.0e30f;  // opacity < 1/255: alpha < 1/255 at every pixel
-                        } else if (det > 1e-3f * (cvx * cvz) && cvx > 0.0f && cvz > 0.0f) {
-                            const float tt = 2.0f * (t + 0.02f);
-                            ext_x = sqrtf(tt * cvx) * 1.0002f + 0.02f;
-                            ext_y = sqrtf(tt * cvz) * 1.0002f + 0.02f;
-                        }
-                        float4* geo = reinterpret_cast<float4*>(a.out.geo + i);
-                        geo[0] = make_float4(px, py, cvz * det_inv, -cvy * det_inv);
-                        geo[1] = make_float4(cvx * det_inv, po.w, ext_x, ext_y);
-                        a.out.depth_radius[i] = make_float2(vz, radius);
-                    }
-                }
+                for (int q = 0; q < 16; ++q) { vm_l[q] = __ldg(a.vm + e * 16 + q); pm_l[q] = __ldg(a.pm + e * 16 + q); }
+                pr[k] = project_one(a, i, po[k], ca[k], cb[k], vm_l, pm_l, s_v, s_focal, gx, gy);
             }
         }
     }
 
-    // ---- partition-local exclusive scan of (visible, pairs) -----------------------------------------
-    const uint64_t mine = ((uint64_t)(count != 0) << 32) | count;
-    uint64_t incl = mine;
+    // ---- depth range of the frame (drives the sort's key compaction, sort.cu KeyXform) --------------------------------
+    {
+        uint32_t dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint64_t up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (uint32_t)d) incl += up;
+        for (uint32_t k = 0; k < PRE_ITEMS; ++k)
+            if (pr[k].count != 0) { dmin = min(dmin, pr[k].depth_bits); dmax = max(dmax, pr[k].depth_bits); }
+        dmin = __reduce_min_sync(0xffffffffu, dmin);
+        dmax = __reduce_max_sync(0xffffffffu, dmax);
+        if (lane == 0 && dmax >= dmin) {  // after the first partitions the range rarely widens: test before the atomic
+            if (dmax > ld_relaxed_u32(&a.ctl->depth_max)) atomicMax(&a.ctl->depth_max, dmax);
+            if (~dmin > ld_relaxed_u32(&a.ctl->inv_depth_min)) atomicMax(&a.ctl->inv_depth_min, ~dmin);
+        }
     }
-    if (lane == 31) s_warp_tot[warp] = incl;
-    s_xy[tid] = rect_xy;
-    s_w[tid] = rect_w;
-    s_depth[tid] = depth_bits;
+
+    // ---- partition-local exclusive scan of (visible, pairs); group k = Gaussians [k*256, (k+1)*256) of the partition ----
+    uint64_t mine[PRE_ITEMS], incl[PRE_ITEMS];
+#pragma unroll
+    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
+        mine[k] = ((uint64_t)(pr[k].count != 0) << 32) | pr[k].count;
+        incl[k] = mine[k];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t up = __shfl_up_sync(0xffffffffu, incl[k], d);
+            if (lane >= (uint32_t)d) incl[k] += up;
+        }
+        if (lane == 31) s_warp_tot[k][warp] = incl[k];
+        const uint32_t slot = k * PRE_THREADS + tid;
+        s_xy[slot] = pr[k].rect_xy;
+        s_w[slot] = pr[k].rect_w;
+        s_depth[slot] = pr[k].depth_bits;
+    }
     __syncthreads();
-    uint64_t warp_excl = 0, total = 0;
+    uint64_t total = 0;  // running (visible, pairs) total of the groups handled so far
+    uint32_t local_excl[PRE_ITEMS];
 #pragma unroll
-    for (uint32_t w = 0; w < PRE_THREADS / 32; ++w) {
-        const uint64_t t = s_warp_tot[w];
-        if (w < warp) warp_excl += t;
-        total += t;
+    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
+        uint64_t warp_excl = 0, group_total = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < PRE_THREADS / 32; ++w) {
+            const uint64_t t = s_warp_tot[k][w];
+            if (w < warp) warp_excl += t;
+            group_total += t;
+        }
+        local_excl[k] = (uint32_t)(total + warp_excl + incl[k] - mine[k]);
+        s_off[k * PRE_THREADS + tid] = local_excl[k];
+        total += group_total;
     }
-    const uint32_t local_excl = (uint32_t)(warp_excl + incl - mine);
-    s_off[tid] = local_excl;
 
     // ---- decoupled look-back across partitions (warp 0) ---------------------------------------------
-    const uint32_t num_parts = (n + PRE_THREADS - 1) / PRE_THREADS;
+    const uint32_t num_parts = (n + PRE_PART - 1) / PRE_PART;
     if (warp == 0) {
         uint64_t exclusive = 0;
         if (part == 0) {
@@ -353,14 +398,16 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunc
     }
     __syncthreads();
     const uint32_t base = (uint32_t)s_base;
-    if (i < n) a.out.offsets[i] = base + local_excl;
+#pragma unroll
+    for (uint32_t k = 0; k < PRE_ITEMS; ++k)
+        if (first + k * PRE_THREADS < n) a.out.offsets[first + k * PRE_THREADS] = base + local_excl[k];
 
     // ---- duplication: the partition's pairs are emitted cooperatively, coalesced ---------------------
     const uint32_t part_pairs = (uint32_t)total;
     for (uint32_t j = tid; j < part_pairs; j += PRE_THREADS) {
         uint32_t g = 0;
 #pragma unroll
-        for (uint32_t step = PRE_THREADS / 2; step >= 1; step >>= 1)
+        for (uint32_t step = PRE_PART / 2; step >= 1; step >>= 1)
             if (s_off[g + step] <= j) g += step;
         const uint32_t r = j - s_off[g];
         const uint32_t w = s_w[g], xy = s_xy[g];
@@ -369,14 +416,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunc
         const uint32_t out = base + j;
         if (out < a.capacity) {
             a.keys[out] = ((uint64_t)tile << 32) | s_depth[g];
-            a.vals[out] = part * PRE_THREADS + g;
+            a.vals[out] = part * PRE_PART + g;
         }
     }
 }
 
 cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s) {
     if (a.scene.n == 0) return cudaSuccess;
-    preprocess_kernel<<<(a.scene.n + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(a);
+    preprocess_kernel<<<(a.scene.n + PRE_PART - 1) / PRE_PART, PRE_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 

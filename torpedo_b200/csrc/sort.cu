@@ -18,13 +18,31 @@ constexpr uint32_t HIST_KPT = 8;
 constexpr uint32_t LOOKBACK_VALUE_MASK = (1u << 30) - 1u;
 constexpr uint32_t LOOKBACK_BATCH = 8;
 
-__device__ __forceinline__ uint32_t digit_of(uint64_t key, uint32_t shift, uint32_t mask) {
-    return (uint32_t)(key >> shift) & mask;
+// Order-preserving key compaction (frame path): keys are tile << 32 | float_bits(viewZ) with viewZ confined to
+// [min, max] of the frame, so the passes sort on  tile << depth_bits | (depth - min)  instead — at 1080p with the default
+// near/far planes that is 27 + 13 = 40 bits = 5 passes instead of 6. The stored keys are never modified.
+struct KeyXform {
+    uint32_t bias, depth_bits, total_bits;
+};
+__device__ __forceinline__ KeyXform make_xform(uint32_t depth_min, uint32_t depth_max, uint32_t end_bit, bool frame_keys) {
+    KeyXform x;
+    if (!frame_keys) { x.bias = 0; x.depth_bits = min(end_bit, 32u); x.total_bits = end_bit; return x; }
+    x.bias = depth_max >= depth_min ? depth_min : 0u;
+    const uint32_t span = depth_max >= depth_min ? depth_max - depth_min : 0u;
+    x.depth_bits = 32u - __clz(span);           // 0 when every key carries the same depth
+    x.total_bits = x.depth_bits + (end_bit - 32u);
+    return x;
 }
-__host__ __device__ __forceinline__ uint32_t pass_mask(uint32_t pass, uint32_t end_bit) {
-    const uint32_t left = end_bit - pass * SORT_RADIX_BITS;
+__device__ __forceinline__ uint32_t digit_of(uint64_t key, const KeyXform& x, uint32_t shift, uint32_t mask) {
+    const uint32_t lo = (uint32_t)key - x.bias, hi = (uint32_t)(key >> 32);
+    const uint64_t packed = x.depth_bits >= 32u ? (((uint64_t)hi << 32) | lo) : (((uint64_t)hi << x.depth_bits) | lo);
+    return (uint32_t)(packed >> shift) & mask;
+}
+__device__ __forceinline__ uint32_t pass_mask(uint32_t pass, uint32_t total_bits) {
+    const uint32_t left = total_bits > pass * SORT_RADIX_BITS ? total_bits - pass * SORT_RADIX_BITS : 0u;
     return left >= SORT_RADIX_BITS ? (SORT_BINS - 1u) : ((1u << left) - 1u);
 }
+__device__ __forceinline__ uint32_t passes_needed(uint32_t total_bits) { return (total_bits + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS; }
 
 // ---------------------------------------------------------------------------------------------------
 // up-front histogram of every digit (one read of the keys)
@@ -35,6 +53,8 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
                                                                   uint32_t end_bit) {
     __shared__ uint32_t h[SORT_MAX_PASSES][SORT_BINS];
     const uint32_t n = n_host == UINT32_MAX ? min(ctl->pairs_total, capacity) : n_host;
+    const KeyXform xf = make_xform(~ctl->inv_depth_min, ctl->depth_max, end_bit, n_host == UINT32_MAX);
+    num_passes = min(num_passes, passes_needed(xf.total_bits));  // passes above the packed key width see a single bin
     for (uint32_t k = threadIdx.x; k < num_passes * SORT_BINS; k += HIST_THREADS) (&h[0][0])[k] = 0;
     __syncthreads();
     const uint32_t chunk = HIST_THREADS * HIST_KPT;
@@ -50,7 +70,7 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
             const uint32_t idx = base + j * HIST_THREADS + threadIdx.x;
             if (idx < n) {
                 for (uint32_t p = 0; p < num_passes; ++p)
-                    atomicAdd(&h[p][digit_of(k[j], p * SORT_RADIX_BITS, pass_mask(p, end_bit))], 1u);
+                    atomicAdd(&h[p][digit_of(k[j], xf, p * SORT_RADIX_BITS, pass_mask(p, xf.total_bits))], 1u);
             }
         }
     }
@@ -66,11 +86,13 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
 // ---------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, SortPlan* plan, uint32_t n_host, uint32_t capacity,
-                                                               uint32_t num_passes) {
+                                                               uint32_t num_passes, uint32_t end_bit) {
     __shared__ uint32_t s_warp[SORT_BINS / 32];
     __shared__ uint32_t s_skip[SORT_MAX_PASSES];
     const uint32_t n = n_host == UINT32_MAX ? min(ctl->pairs_total, capacity) : n_host;
     const uint32_t b = threadIdx.x, lane = b & 31u, warp = b >> 5;
+    const KeyXform xf = make_xform(~ctl->inv_depth_min, ctl->depth_max, end_bit, n_host == UINT32_MAX);
+    num_passes = min(num_passes, passes_needed(xf.total_bits));
     if (b < SORT_MAX_PASSES) s_skip[b] = 0;
     __syncthreads();
     for (uint32_t p = 0; p < num_passes; ++p) {
@@ -101,6 +123,9 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, Sor
         plan->num_passes = num_passes;
         plan->final_sel = sel;
         plan->passes_run = run;
+        plan->bias = xf.bias;
+        plan->depth_bits = xf.depth_bits;
+        plan->total_bits = xf.total_bits;
     }
 }
 
@@ -123,7 +148,7 @@ static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phas
 //   stable ranking (match.any) + key scatter to smem | look-back per bin | coalesced key write-out, value scatter | value write-out
 __global__ void __launch_bounds__(SORT_THREADS, 3)
 onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, FrameCtl* ctl,
-                const SortPlan* __restrict__ plan, uint32_t* lookback_pass, uint32_t pass, uint32_t end_bit) {
+                const SortPlan* __restrict__ plan, uint32_t* lookback_pass, uint32_t pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
 
@@ -148,7 +173,8 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     const uint32_t* __restrict__ src_vals = src ? vals1 : vals0;
     uint64_t* __restrict__ dst_keys = src ? keys0 : keys1;
     uint32_t* __restrict__ dst_vals = src ? vals0 : vals1;
-    const uint32_t shift = pass * SORT_RADIX_BITS, mask = pass_mask(pass, end_bit);
+    const KeyXform xf{ plan->bias, plan->depth_bits, plan->total_bits };
+    const uint32_t shift = pass * SORT_RADIX_BITS, mask = pass_mask(pass, xf.total_bits);
 
     // ---- load (warp-striped: item k of lane l sits at warp_base + 32k + l) --------------------------
     uint64_t key[SORT_KPT];
@@ -161,9 +187,24 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = (warp_base + k * 32u) < n ? src_keys[warp_base + k * 32u] : ~0ull;  // padding sorts last
     }
 
+    // ---- digits, computed once and packed four to a register; padding (only in the last tile) goes to the top bin -------
+    uint32_t dpack[SORT_KPT / 4];
+#pragma unroll
+    for (uint32_t q = 0; q < SORT_KPT / 4; ++q) {
+        uint32_t w = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < 4; ++r) {
+            const uint32_t k = q * 4 + r;
+            const bool valid = n_valid == SORT_TILE || (warp_base + k * 32u) < n;
+            w |= (valid ? digit_of(key[k], xf, shift, mask) : mask) << (8u * r);
+        }
+        dpack[q] = w;
+    }
+    auto digit_at = [&](uint32_t k) { return (dpack[k >> 2] >> (8u * (k & 3u))) & 0xffu; };
+
     // ---- early counts: per-warp digit histograms ----------------------------------------------------
 #pragma unroll
-    for (uint32_t k = 0; k < SORT_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_of(key[k], shift, mask)], 1u);
+    for (uint32_t k = 0; k < SORT_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_at(k)], 1u);
     __syncthreads();
 
     // ---- per-bin (thread == bin): exclusive prefix over warps, publish the tile aggregate, scan the bins -------------
@@ -197,7 +238,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     uint32_t rank[SORT_KPT];
 #pragma unroll
     for (uint32_t k = 0; k < SORT_KPT; ++k) {
-        const uint32_t d = digit_of(key[k], shift, mask);
+        const uint32_t d = digit_at(k);
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const uint32_t lower = __popc(peers & lanemask_lt());
         const uint32_t base = sm.warp_hist[warp][d];
@@ -255,7 +296,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         const uint32_t i = tid + k * SORT_THREADS;
         if (i < n_valid) {
             const uint64_t kk = sm.keys[i];
-            pos[k] = sm.global_base[digit_of(kk, shift, mask)] + i;
+            pos[k] = sm.global_base[digit_of(kk, xf, shift, mask)] + i;
             dst_keys[pos[k]] = kk;
         }
     }
@@ -292,7 +333,7 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     const uint32_t num_passes = (a.end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
     const uint32_t bound = n_host == UINT32_MAX ? a.capacity : n_host;
     if (bound == 0 || num_passes == 0) {
-        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host == UINT32_MAX ? UINT32_MAX : 0u, a.capacity, 0);
+        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host == UINT32_MAX ? UINT32_MAX : 0u, a.capacity, 0, a.end_bit);
         if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
         return cudaGetLastError();
     }
@@ -301,13 +342,13 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     const uint32_t hist_max = (uint32_t)a.sm_count * 4u;
     if (hist_grid > hist_max) hist_grid = hist_max;
     sort_hist_kernel<<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.ctl, n_host, a.capacity, num_passes, a.end_bit);
-    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host, a.capacity, num_passes);
+    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host, a.capacity, num_passes, a.end_bit);
     if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
     const uint32_t parts = sort_parts(bound);
     const uint32_t parts_cap = sort_parts(a.capacity);
     for (uint32_t p = 0; p < num_passes; ++p) {
         onesweep_kernel<<<parts, SORT_THREADS, sizeof(OnesweepSmem), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan,
-                                                                          a.lookback + (size_t)p * parts_cap * SORT_BINS, p, a.end_bit);
+                                                                          a.lookback + (size_t)p * parts_cap * SORT_BINS, p);
     }
     return cudaGetLastError();
 }

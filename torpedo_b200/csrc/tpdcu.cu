@@ -154,7 +154,7 @@ static int ensure_zero_region(tpdcu_ctx* c, uint32_t passes) {
     if (c->zero_region && c->zero_n == c->n && c->zero_capacity == c->capacity && c->zero_tiles == tiles) return TPDCU_OK;
     cudaFree(c->zero_region);
     c->zero_region = nullptr;
-    const uint32_t pre_parts = (c->n + PRE_THREADS - 1) / PRE_THREADS;
+    const uint32_t pre_parts = (c->n + PRE_PART - 1) / PRE_PART;
     size_t off = align_up(sizeof(FrameCtl), 256);
     c->off_scan_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
     c->off_ranges = off;    off = align_up(off + (size_t)tiles * 2 * sizeof(uint32_t), 256);
