@@ -40,17 +40,21 @@ cudaError_t launch_ranges(const RasterLaunch& a, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// blend: one CTA per 16x16 tile; 64 threads, each owning a 2x2 pixel block, so the per-splat shared-memory reads, loop
-// overhead and the dx/dy terms of the quadratic form are shared by four pixels. Splats are staged through shared memory in
-// sorted order; while staging, splats whose alpha >= 1/255 region (SplatGeo::ext_*) cannot reach the tile are dropped —
-// every pixel would `continue` on them (blend.slang:85,89), so dropping them leaves the result unchanged while removing
-// about a quarter of the (pixel, splat) evaluations. The conic is pre-scaled by -0.5*log2(e) at staging so that
-// alpha = opacity * ex2(power2).
+// blend: one CTA per 16x16 tile, four warps = four 8x8 pixel quadrants, each lane owning two horizontally adjacent pixels.
+//
+// Splats are staged through shared memory in sorted order. While staging, the conservative bounding box of each splat's
+// alpha >= 1/255 region (SplatGeo::ext_*, written by the preprocess kernel) is tested against the tile and against each
+// quadrant: a splat that cannot reach a quadrant is never seen by that quadrant's warp (every pixel would `continue` on
+// it, blend.slang:85,89, so the result is unchanged). On the headline scene the warps iterate over ~35 % of the
+// (splat, pixel) pairs the reference evaluates. Each warp walks its own in-order list of queue entries; the conic is
+// pre-scaled by -0.5*log2(e) at staging so that alpha = opacity * ex2(p).
 // ---------------------------------------------------------------------------------------------------
 
-constexpr uint32_t BLEND_THREADS = 64;
+constexpr uint32_t BLEND_THREADS = 128;
+constexpr uint32_t BLEND_WARPS = BLEND_THREADS / 32;
 constexpr uint32_t BLEND_QUEUE = 256;
 constexpr float LOG2E = 1.4426950408889634f;
+static_assert(BLEND_WARPS == 4, "one warp per 8x8 quadrant of the 16x16 tile");
 
 __device__ __forceinline__ uint32_t unorm8(float c) {
     // clamp to [0,1] (NaN -> 0), x255, round to nearest even: the R8G8B8A8_UNORM image store
@@ -64,17 +68,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(BLEND_THREADS) blend_kernel(RasterLaunch a) {
-    __shared__ float4 s_g0[BLEND_QUEUE];   // px, py, A', B'
-    __shared__ float4 s_g1[BLEND_QUEUE];   // C', opacity, power2 threshold, -
-    __shared__ float4 s_col[BLEND_QUEUE];  // r, g, b
-    __shared__ uint32_t s_cnt[BLEND_THREADS / 32];
+struct BlendSmem {
+    float4 g0[BLEND_QUEUE];                      // px, py, A', B'
+    float4 g1[BLEND_QUEUE];                      // C', opacity, power2 threshold, -
+    float4 col[BLEND_QUEUE];                     // r, g, b
+    uint16_t list[BLEND_WARPS][BLEND_QUEUE];     // per-quadrant queue entry indices, in sorted order
+    uint32_t cnt[BLEND_WARPS][BLEND_WARPS + 1];  // [staging warp][tile, quadrant 0..3] survivors of the current round
+};
+
+__global__ void __launch_bounds__(BLEND_THREADS, 10) blend_kernel(RasterLaunch a) {
+    __shared__ BlendSmem sm;
 
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX;
     const uint32_t tile = blockIdx.x;
     const uint32_t tile_x0 = (tile % gx) * TILE_PX, tile_y0 = (tile / gx) * TILE_PX;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t x0 = tile_x0 + 2u * (tid & 7u), y0 = tile_y0 + 2u * (tid >> 3);
+    // quadrant `warp`: origin (8*(warp&1), 8*(warp>>1)); lane -> pixel pair at (2*(lane&3), lane>>2) inside it
+    const uint32_t x0 = tile_x0 + 8u * (warp & 1u) + 2u * (lane & 3u), y0 = tile_y0 + 8u * (warp >> 1) + (lane >> 2);
     const float fx0 = (float)x0, fy0 = (float)y0;
     const float tile_fx0 = (float)tile_x0, tile_fy0 = (float)tile_y0;
 
@@ -82,83 +92,111 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_kernel(RasterLaunch a) {
     const uint2 range = reinterpret_cast<const uint2*>(a.ranges)[tile];
     const float4* __restrict__ geo4 = reinterpret_cast<const float4*>(a.geo);
 
-    // pixel k = (x0 + (k & 1), y0 + (k >> 1)); `live` bit k: still accumulating
-    uint32_t live = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < 4; ++k)
-        if (x0 + (k & 1u) < a.width && y0 + (k >> 1) < a.height) live |= 1u << k;
+    uint32_t live = 0;  // bit k: pixel (x0 + k, y0) is still accumulating
+    if (y0 < a.height) {
+        if (x0 < a.width) live |= 1u;
+        if (x0 + 1u < a.width) live |= 2u;
+    }
     const uint32_t inside = live;
-    float T[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
-    float cr[4] = { 0.f, 0.f, 0.f, 0.f }, cg[4] = { 0.f, 0.f, 0.f, 0.f }, cb[4] = { 0.f, 0.f, 0.f, 0.f };
+    float T0 = 1.0f, T1 = 1.0f, r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
 
     uint32_t in = range.x;
     while (true) {
-        // ---- fill: append the next splats that can touch this tile, in order -----------------------------------------
-        uint32_t qn = 0;
+        // ---- fill: append the next splats that can touch this tile / each quadrant, in order --------------------------
+        uint32_t qn = 0;                                // queue entries
+        uint32_t ln[BLEND_WARPS] = { 0u, 0u, 0u, 0u };  // list length of every quadrant (uniform across the CTA)
         while (qn + BLEND_THREADS <= BLEND_QUEUE && in < range.y) {
             const uint32_t idx = in + tid;
-            bool keep = false;
+            uint32_t keep = 0;  // bit 0: tile, bits 1..4: quadrants 0..3
             uint32_t g = 0;
-            float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
             if (idx < range.y) {
                 g = __ldg(vals + idx);
-                r0 = __ldg(geo4 + (size_t)g * 2);
-                r1 = __ldg(geo4 + (size_t)g * 2 + 1);
-                keep = (r0.x + r1.z >= tile_fx0) && (r0.x - r1.z <= tile_fx0 + 15.0f) && (r0.y + r1.w >= tile_fy0) &&
-                       (r0.y - r1.w <= tile_fy0 + 15.0f);
+                ra = __ldg(geo4 + (size_t)g * 2);
+                rb = __ldg(geo4 + (size_t)g * 2 + 1);
+                const float xlo = ra.x - rb.z - tile_fx0, xhi = ra.x + rb.z - tile_fx0;  // bbox relative to the tile origin
+                const float ylo = ra.y - rb.w - tile_fy0, yhi = ra.y + rb.w - tile_fy0;
+                const bool left = xhi >= 0.0f && xlo <= 7.0f, right = xhi >= 8.0f && xlo <= 15.0f;
+                const bool top = yhi >= 0.0f && ylo <= 7.0f, bottom = yhi >= 8.0f && ylo <= 15.0f;
+                keep = ((left && top) ? 2u : 0u) | ((right && top) ? 4u : 0u) | ((left && bottom) ? 8u : 0u) |
+                       ((right && bottom) ? 16u : 0u);
+                if (keep) keep |= 1u;
             }
-            const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) s_cnt[warp] = __popc(ballot);
+            uint32_t ballot[BLEND_WARPS + 1];
+#pragma unroll
+            for (uint32_t q = 0; q <= BLEND_WARPS; ++q) {
+                ballot[q] = __ballot_sync(0xffffffffu, (keep >> q) & 1u);
+                if (lane == q) sm.cnt[warp][q] = __popc(ballot[q]);
+            }
             __syncthreads();
-            const uint32_t c0 = s_cnt[0], c1 = s_cnt[1];
-            if (keep) {
-                const uint32_t pos = qn + (warp ? c0 : 0u) + __popc(ballot & lanemask_lt());
-                const float4 col = __ldg(a.color + g);
-                s_g0[pos] = make_float4(r0.x, r0.y, (-0.5f * LOG2E) * r0.z, -LOG2E * r0.w);
-                s_g1[pos] = make_float4((-0.5f * LOG2E) * r1.x, r1.y, -__log2f(255.0f * r1.y) - 0.01f, 0.0f);
-                s_col[pos] = col;
+            uint32_t before[BLEND_WARPS + 1], total[BLEND_WARPS + 1];
+#pragma unroll
+            for (uint32_t q = 0; q <= BLEND_WARPS; ++q) {
+                before[q] = 0;
+                total[q] = 0;
+#pragma unroll
+                for (uint32_t w = 0; w < BLEND_WARPS; ++w) {
+                    const uint32_t c = sm.cnt[w][q];
+                    if (w < warp) before[q] += c;
+                    total[q] += c;
+                }
             }
-            qn += c0 + c1;
+            if (keep) {
+                const uint32_t pos = qn + before[0] + __popc(ballot[0] & lanemask_lt());
+                const float4 col = __ldg(a.color + g);
+                sm.g0[pos] = make_float4(ra.x, ra.y, (-0.5f * LOG2E) * ra.z, -LOG2E * ra.w);
+                sm.g1[pos] = make_float4((-0.5f * LOG2E) * rb.x, rb.y, -__log2f(255.0f * rb.y) - 0.01f, 0.0f);
+                sm.col[pos] = col;
+#pragma unroll
+                for (uint32_t q = 0; q < BLEND_WARPS; ++q)
+                    if (keep & (2u << q)) sm.list[q][ln[q] + before[q + 1] + __popc(ballot[q + 1] & lanemask_lt())] = (uint16_t)pos;
+            }
+            qn += total[0];
+#pragma unroll
+            for (uint32_t q = 0; q < BLEND_WARPS; ++q) ln[q] += total[q + 1];
             in += BLEND_THREADS;
             __syncthreads();
         }
 
-        // ---- drain: front-to-back compositing (blend.slang:77-100) for the four pixels of this thread ----------------
-        for (uint32_t j = 0; j < qn && live; ++j) {
-            const float4 g0 = s_g0[j];
-            const float4 g1 = s_g1[j];
-            const float dx0 = g0.x - fx0, dy0 = g0.y - fy0;
-            const float dx1 = dx0 - 1.0f, dy1 = dy0 - 1.0f;
-            const float ax0 = g0.z * dx0, ax1 = g0.z * dx1;
-            const float by0 = g0.w * dy0, by1 = g0.w * dy1;
-            const float cy0 = g1.x * dy0 * dy0, cy1 = g1.x * dy1 * dy1;
-            float p[4];
-            p[0] = fmaf(dx0, ax0 + by0, cy0);
-            p[1] = fmaf(dx1, ax1 + by0, cy0);
-            p[2] = fmaf(dx0, ax0 + by1, cy1);
-            p[3] = fmaf(dx1, ax1 + by1, cy1);
-            uint32_t hit = 0;
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k)
-                if (p[k] <= 0.0f && p[k] >= g1.z) hit |= 1u << k;
-            hit &= live;
-            if (hit == 0) continue;
-            const float4 c = s_col[j];
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {
-                if (hit & (1u << k)) {
-                    const float alpha = fminf(0.99f, g1.y * ex2_approx(p[k]));
-                    if (alpha >= 1.0f / 255.0f) {
-                        const float test_T = T[k] * (1.0f - alpha);
-                        if (test_T < 0.0001f) {
-                            live &= ~(1u << k);  // done; this splat is NOT added (blend.slang:92-95)
-                        } else {
-                            const float w = alpha * T[k];
-                            cr[k] = fmaf(c.x, w, cr[k]);
-                            cg[k] = fmaf(c.y, w, cg[k]);
-                            cb[k] = fmaf(c.z, w, cb[k]);
-                            T[k] = test_T;
-                        }
+        // ---- drain: front-to-back compositing (blend.slang:77-100) over this quadrant's list --------------------------
+        const uint32_t my_ln = warp == 0 ? ln[0] : warp == 1 ? ln[1] : warp == 2 ? ln[2] : ln[3];
+        const uint16_t* my_list = sm.list[warp];
+        for (uint32_t j = 0; j < my_ln; ++j) {
+            if (__all_sync(0xffffffffu, live == 0)) break;          // the whole quadrant is done (every lane votes here)
+            const uint32_t e = my_list[j];
+            const float4 q0 = sm.g0[e];
+            const float4 q1 = sm.g1[e];
+            const float dx0 = q0.x - fx0, dy = q0.y - fy0;
+            const float dx1 = dx0 - 1.0f;
+            const float by = q0.w * dy;
+            const float cy = q1.x * dy * dy;
+            const float p0 = fmaf(dx0, fmaf(q0.z, dx0, by), cy);   // A'dx^2 + B'dx dy + C'dy^2 = log2(e) * power
+            const float p1 = fmaf(dx1, fmaf(q0.z, dx1, by), cy);
+            if (fmaxf(p0, p1) < q1.z) continue;                     // alpha < 1/255 at both pixels (blend.slang:89)
+            const float4 c = sm.col[e];
+            if ((live & 1u) && p0 <= 0.0f) {                        // power > 0 is skipped (blend.slang:85)
+                const float alpha = fminf(0.99f, q1.y * ex2_approx(p0));
+                if (alpha >= 1.0f / 255.0f) {
+                    const float test_T = T0 * (1.0f - alpha);
+                    if (test_T < 0.0001f) {
+                        live &= ~1u;                                // done; this splat is NOT added (blend.slang:92-95)
+                    } else {
+                        const float w = alpha * T0;
+                        r0 = fmaf(c.x, w, r0); g0 = fmaf(c.y, w, g0); b0 = fmaf(c.z, w, b0);
+                        T0 = test_T;
+                    }
+                }
+            }
+            if ((live & 2u) && p1 <= 0.0f) {
+                const float alpha = fminf(0.99f, q1.y * ex2_approx(p1));
+                if (alpha >= 1.0f / 255.0f) {
+                    const float test_T = T1 * (1.0f - alpha);
+                    if (test_T < 0.0001f) {
+                        live &= ~2u;
+                    } else {
+                        const float w = alpha * T1;
+                        r1 = fmaf(c.x, w, r1); g1 = fmaf(c.y, w, g1); b1 = fmaf(c.z, w, b1);
+                        T1 = test_T;
                     }
                 }
             }
@@ -168,13 +206,12 @@ __global__ void __launch_bounds__(BLEND_THREADS) blend_kernel(RasterLaunch a) {
         if (__syncthreads_and(live == 0) || finished) break;
     }
 
-#pragma unroll
-    for (uint32_t k = 0; k < 4; ++k) {
-        if (inside & (1u << k)) {
-            const uint32_t rgba = unorm8(cr[k]) | (unorm8(cg[k]) << 8) | (unorm8(cb[k]) << 16) | 0xff000000u;
-            *reinterpret_cast<uint32_t*>(a.out + (size_t)(y0 + (k >> 1)) * a.pitch + (size_t)(x0 + (k & 1u)) * 4) = rgba;
-        }
-    }
+    if (inside & 1u)
+        *reinterpret_cast<uint32_t*>(a.out + (size_t)y0 * a.pitch + (size_t)x0 * 4) =
+            unorm8(r0) | (unorm8(g0) << 8) | (unorm8(b0) << 16) | 0xff000000u;
+    if (inside & 2u)
+        *reinterpret_cast<uint32_t*>(a.out + (size_t)y0 * a.pitch + (size_t)(x0 + 1u) * 4) =
+            unorm8(r1) | (unorm8(g1) << 8) | (unorm8(b1) << 16) | 0xff000000u;
 }
 
 cudaError_t launch_blend(const RasterLaunch& a, cudaStream_t s) {
