@@ -76,7 +76,7 @@ struct BlendSmem {
     uint32_t cnt[BLEND_WARPS][BLEND_WARPS + 1];  // [staging warp][tile, quadrant 0..3] survivors of the current round
 };
 
-__global__ void __launch_bounds__(BLEND_THREADS, 10) blend_kernel(RasterLaunch a) {
+__global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a) {
     __shared__ BlendSmem sm;
 
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 10) blend_kernel(RasterLaunch a
         const uint32_t my_ln = warp == 0 ? ln[0] : warp == 1 ? ln[1] : warp == 2 ? ln[2] : ln[3];
         const uint16_t* my_list = sm.list[warp];
         for (uint32_t j = 0; j < my_ln; ++j) {
-            if (__all_sync(0xffffffffu, live == 0)) break;          // the whole quadrant is done (every lane votes here)
+            if ((j & 7u) == 0u && __all_sync(0xffffffffu, live == 0)) break;  // the whole quadrant is done (uniform branch)
             const uint32_t e = my_list[j];
             const float4 q0 = sm.g0[e];
             const float4 q1 = sm.g1[e];
