@@ -14,8 +14,14 @@ constexpr uint32_t SH_PLANES = 12;        // 48 SH floats as 12 float4 planes
 constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
+#ifndef TPDCU_SORT_KPT
+#define TPDCU_SORT_KPT 16
+#endif
+#ifndef TPDCU_SORT_MINB
+#define TPDCU_SORT_MINB 3
+#endif
 constexpr uint32_t SORT_THREADS = 256;
-constexpr uint32_t SORT_KPT = 16;         // keys per thread
+constexpr uint32_t SORT_KPT = TPDCU_SORT_KPT;  // keys per thread
 constexpr uint32_t SORT_TILE = SORT_THREADS * SORT_KPT;
 constexpr uint32_t SORT_WARPS = SORT_THREADS / 32;
 

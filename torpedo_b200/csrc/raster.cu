@@ -16,25 +16,39 @@ __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
     const uint32_t n = a.plan->n;
     const uint64_t* __restrict__ keys = a.plan->final_sel ? a.keys[1] : a.keys[0];
     uint2* ranges = reinterpret_cast<uint2*>(a.ranges);
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-        const uint32_t curr = (uint32_t)(keys[idx] >> 32);
+    // two keys per thread with one 16-byte load; the key before the pair comes from the neighbour's line (L1 hit)
+    const uint32_t pairs2 = (n + 1) / 2;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < pairs2; t += gridDim.x * blockDim.x) {
+        const uint32_t idx = 2 * t;
+        uint64_t k0, k1 = 0;
+        if (idx + 1 < n) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(keys) + t);
+            k0 = v.x;
+            k1 = v.y;
+        } else {
+            k0 = keys[idx];
+        }
+        const uint32_t t0 = (uint32_t)(k0 >> 32);
         if (idx == 0) {
-            ranges[curr].x = 0;
+            ranges[t0].x = 0;
         } else {
             const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
-            if (curr != prev) {
-                ranges[prev].y = idx;
-                ranges[curr].x = idx;
-            }
+            if (t0 != prev) { ranges[prev].y = idx; ranges[t0].x = idx; }
         }
-        if (idx == n - 1) ranges[curr].y = idx + 1;
+        if (idx + 1 < n) {
+            const uint32_t t1 = (uint32_t)(k1 >> 32);
+            if (t1 != t0) { ranges[t0].y = idx + 1; ranges[t1].x = idx + 1; }
+            if (idx + 1 == n - 1) ranges[t1].y = n;
+        } else {
+            ranges[t0].y = n;  // idx == n - 1
+        }
     }
 }
 
 cudaError_t launch_ranges(const RasterLaunch& a, cudaStream_t s) {
     if (a.capacity == 0) return cudaSuccess;
-    uint32_t grid = (a.capacity + 255) / 256;
-    if (grid > 148u * 16u) grid = 148u * 16u;
+    uint32_t grid = (a.capacity / 2 + 255) / 256;
+    if (grid > 148u * 8u) grid = 148u * 8u;
     ranges_kernel<<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
 }

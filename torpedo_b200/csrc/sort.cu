@@ -57,20 +57,42 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
     num_passes = min(num_passes, passes_needed(xf.total_bits));  // passes above the packed key width see a single bin
     for (uint32_t k = threadIdx.x; k < num_passes * SORT_BINS; k += HIST_THREADS) (&h[0][0])[k] = 0;
     __syncthreads();
+    // Each thread takes HIST_KPT CONSECUTIVE keys (four 16-byte loads): the pairs of one Gaussian are adjacent in the
+    // unsorted buffer and share their depth bits (and usually the upper tile bits), so run-length encoding the digits in
+    // registers removes most shared-memory atomics and nearly all same-address conflicts.
     const uint32_t chunk = HIST_THREADS * HIST_KPT;
     for (uint32_t base = blockIdx.x * chunk; base < n; base += gridDim.x * chunk) {
+        const uint32_t first = base + threadIdx.x * HIST_KPT;
         uint64_t k[HIST_KPT];
+        if (first + HIST_KPT <= n) {
 #pragma unroll
-        for (uint32_t j = 0; j < HIST_KPT; ++j) {
-            const uint32_t idx = base + j * HIST_THREADS + threadIdx.x;
-            k[j] = idx < n ? __ldg(keys + idx) : 0ull;
+            for (uint32_t j = 0; j < HIST_KPT / 2; ++j) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(keys + first) + j);
+                k[2 * j] = v.x;
+                k[2 * j + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < HIST_KPT; ++j) k[j] = first + j < n ? keys[first + j] : 0ull;
         }
+        const uint32_t valid = first >= n ? 0u : min(HIST_KPT, n - first);
+        if (valid) {
+            for (uint32_t p = 0; p < num_passes; ++p) {
+                const uint32_t shift = p * SORT_RADIX_BITS, mask = pass_mask(p, xf.total_bits);
+                uint32_t run_digit = digit_of(k[0], xf, shift, mask), run = 1;
 #pragma unroll
-        for (uint32_t j = 0; j < HIST_KPT; ++j) {
-            const uint32_t idx = base + j * HIST_THREADS + threadIdx.x;
-            if (idx < n) {
-                for (uint32_t p = 0; p < num_passes; ++p)
-                    atomicAdd(&h[p][digit_of(k[j], xf, p * SORT_RADIX_BITS, pass_mask(p, xf.total_bits))], 1u);
+                for (uint32_t j = 1; j < HIST_KPT; ++j) {
+                    if (j < valid) {
+                        const uint32_t d = digit_of(k[j], xf, shift, mask);
+                        if (d != run_digit) {
+                            atomicAdd(&h[p][run_digit], run);
+                            run_digit = d;
+                            run = 0;
+                        }
+                        ++run;
+                    }
+                }
+                atomicAdd(&h[p][run_digit], run);
             }
         }
     }
@@ -146,7 +168,7 @@ static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phas
 // One CTA = one tile of SORT_TILE pairs. Phases (6 block barriers):
 //   ticket + zero per-warp histograms | load keys (+values), early counts | per-bin: warp prefix, publish aggregate, bin scan |
 //   stable ranking (match.any) + key scatter to smem | look-back per bin | coalesced key write-out, value scatter | value write-out
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+__global__ void __launch_bounds__(SORT_THREADS, TPDCU_SORT_MINB)
 onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, FrameCtl* ctl,
                 const SortPlan* __restrict__ plan, uint32_t* lookback_pass, uint32_t pass) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -155,7 +177,11 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     if (plan->skip[pass]) return;
     const uint32_t n = plan->n;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+#ifdef TPDCU_EXPERIMENT_BLOCKIDX_TICKET
+    if (tid == 0) sm.part = blockIdx.x;
+#else
     if (tid == 0) sm.part = atomicAdd(&ctl->sort_ticket[pass], 1u);
+#endif
     {
         uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[0][0]);
 #pragma unroll
@@ -276,7 +302,13 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
                 for (int j = 0; j < (int)LOOKBACK_BATCH; ++j) {
                     if (!done) {
                         uint32_t x = v[j];
+#ifdef TPDCU_EXPERIMENT_BLOCKIDX_TICKET
+                        for (uint32_t spins = 0; (x >> 30) == FLAG_INVALID && spins < (1u << 20); ++spins)
+                            x = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
+                        if ((x >> 30) == FLAG_INVALID) x = FLAG_PREFIX << 30;  // experiment-only safety valve: never hang
+#else
                         while ((x >> 30) == FLAG_INVALID) x = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
+#endif
                         excl += x & LOOKBACK_VALUE_MASK;
                         done = (x >> 30) == FLAG_PREFIX;  // tile 0 always carries a PREFIX, so look - j never goes below 0 unconsumed
                     }
