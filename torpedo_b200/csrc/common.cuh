@@ -46,7 +46,10 @@ struct SortPlan {
     uint32_t bias;                        // subtracted from the low (depth) word of every key before digit extraction
     uint32_t depth_bits;                  // significant bits of (depth - bias); the tile id is packed right above them
     uint32_t total_bits;                  // depth_bits + tile bits: what the passes actually sort on
-    uint32_t pad;
+    uint32_t idx_bits;                    // packed mode: low bits of every word that hold the Gaussian index (else 0)
+    uint32_t packed;                      // 1: the sorted result is ONE array of packed words (see sort.cu), 0: key/value pairs
+    uint32_t packed_overflow;             // 1: this frame's tile|depth|index does not fit 64 bits -> results invalid, re-render in pair mode
+    uint32_t pad[2];
     uint32_t skip[SORT_MAX_PASSES];       // pass is an identity permutation (single occupied bin)
     uint32_t src_sel[SORT_MAX_PASSES];    // ping-pong buffer the pass reads from
 };
@@ -153,6 +156,7 @@ struct SortLaunch {
     uint32_t* lookback;                   // zeroed, [num_passes][parts_cap][SORT_BINS]
     uint32_t capacity;                    // launch bound for grids
     uint32_t end_bit;                     // 32 + tile bits (frame path) or the caller's end bit (standalone)
+    uint32_t packed_idx_bits;             // 0: pair mode; else bits reserved for the Gaussian index in packed words
     int sm_count;
 };
 // n is taken from ctl->pairs_total clamped to capacity (frame path) when n_host == UINT32_MAX,
@@ -175,6 +179,7 @@ struct RasterLaunch {
 cudaError_t launch_ranges(const RasterLaunch& a, cudaStream_t s);
 cudaError_t launch_blend(const RasterLaunch& a, cudaStream_t s);
 
+cudaError_t launch_sort_unpack(const SortLaunch& a, uint64_t* out_keys, uint32_t* out_vals, cudaStream_t s);
 cudaError_t launch_sort_copy_result(const SortLaunch& a, uint64_t* out_keys, uint32_t* out_vals, uint32_t n, cudaStream_t s);
 
 cudaError_t launch_export_splats(const SplatArrays& a, uint32_t n, void* out48, cudaStream_t s);

@@ -14,7 +14,9 @@ namespace tpdcu {
 
 __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
     const uint32_t n = a.plan->n;
+    if (a.plan->packed_overflow) return;  // this frame is going to be re-rendered in pair mode
     const uint64_t* __restrict__ keys = a.plan->final_sel ? a.keys[1] : a.keys[0];
+    const uint32_t tshift = a.plan->packed ? a.plan->depth_bits + a.plan->idx_bits : 32u;  // tile id sits on top in both formats
     uint2* ranges = reinterpret_cast<uint2*>(a.ranges);
     // two keys per thread with one 16-byte load; the key before the pair comes from the neighbour's line (L1 hit)
     const uint32_t pairs2 = (n + 1) / 2;
@@ -28,15 +30,15 @@ __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
         } else {
             k0 = keys[idx];
         }
-        const uint32_t t0 = (uint32_t)(k0 >> 32);
+        const uint32_t t0 = (uint32_t)(k0 >> tshift);
         if (idx == 0) {
             ranges[t0].x = 0;
         } else {
-            const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+            const uint32_t prev = (uint32_t)(keys[idx - 1] >> tshift);
             if (t0 != prev) { ranges[prev].y = idx; ranges[t0].x = idx; }
         }
         if (idx + 1 < n) {
-            const uint32_t t1 = (uint32_t)(k1 >> 32);
+            const uint32_t t1 = (uint32_t)(k1 >> tshift);
             if (t1 != t0) { ranges[t0].y = idx + 1; ranges[t1].x = idx + 1; }
             if (idx + 1 == n - 1) ranges[t1].y = n;
         } else {
@@ -102,7 +104,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
     const float fx0 = (float)x0, fy0 = (float)y0;
     const float tile_fx0 = (float)tile_x0, tile_fy0 = (float)tile_y0;
 
+    if (a.plan->packed_overflow) return;  // this frame is going to be re-rendered in pair mode
+    const bool packed = a.plan->packed != 0u;
+    const uint32_t idx_mask = packed ? (uint32_t)((1ull << a.plan->idx_bits) - 1ull) : 0xffffffffu;
     const uint32_t* __restrict__ vals = a.plan->final_sel ? a.vals[1] : a.vals[0];
+    const uint64_t* __restrict__ words = a.plan->final_sel ? a.keys[1] : a.keys[0];
     const uint2 range = reinterpret_cast<const uint2*>(a.ranges)[tile];
     const float4* __restrict__ geo4 = reinterpret_cast<const float4*>(a.geo);
 
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
             uint32_t g = 0;
             float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
             if (idx < range.y) {
-                g = __ldg(vals + idx);
+                g = packed ? ((uint32_t)__ldg(words + idx) & idx_mask) : __ldg(vals + idx);
                 ra = __ldg(geo4 + (size_t)g * 2);
                 rb = __ldg(geo4 + (size_t)g * 2 + 1);
                 const float xlo = ra.x - rb.z - tile_fx0, xhi = ra.x + rb.z - tile_fx0;  // bbox relative to the tile origin

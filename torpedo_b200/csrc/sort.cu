@@ -17,6 +17,13 @@ constexpr uint32_t HIST_THREADS = 512;
 constexpr uint32_t HIST_KPT = 8;
 constexpr uint32_t LOOKBACK_VALUE_MASK = (1u << 30) - 1u;
 constexpr uint32_t LOOKBACK_BATCH = 8;
+#ifndef TPDCU_SORT_PREFETCH_TILES
+#define TPDCU_SORT_PREFETCH_TILES 296
+#endif
+#ifndef TPDCU_SORT_MINB_PACKED
+#define TPDCU_SORT_MINB_PACKED 4
+#endif
+constexpr uint32_t SORT_PREFETCH_TILES = TPDCU_SORT_PREFETCH_TILES;  // 148 SMs x 3 resident CTAs
 
 // Order-preserving key compaction (frame path): keys are tile << 32 | float_bits(viewZ) with viewZ confined to
 // [min, max] of the frame, so the passes sort on  tile << depth_bits | (depth - min)  instead — at 1080p with the default
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
 // ---------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, SortPlan* plan, uint32_t n_host, uint32_t capacity,
-                                                               uint32_t num_passes, uint32_t end_bit) {
+                                                               uint32_t num_passes, uint32_t end_bit, uint32_t packed_idx_bits) {
     __shared__ uint32_t s_warp[SORT_BINS / 32];
     __shared__ uint32_t s_skip[SORT_MAX_PASSES];
     const uint32_t n = n_host == UINT32_MAX ? min(ctl->pairs_total, capacity) : n_host;
@@ -135,8 +142,10 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, Sor
     }
     if (b == 0) {
         uint32_t sel = 0, run = 0;
+        const bool packed = packed_idx_bits != 0u;
         for (uint32_t p = 0; p < SORT_MAX_PASSES; ++p) {
-            const uint32_t skip = p < num_passes ? s_skip[p] : 1u;
+            uint32_t skip = p < num_passes ? s_skip[p] : 1u;
+            if (packed && p == 0 && n > 0) skip = 0;  // the first pass also converts pairs to packed words: never skipped
             plan->skip[p] = skip;
             plan->src_sel[p] = sel;
             if (!skip) { sel ^= 1u; ++run; }
@@ -148,6 +157,10 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, Sor
         plan->bias = xf.bias;
         plan->depth_bits = xf.depth_bits;
         plan->total_bits = xf.total_bits;
+        plan->idx_bits = packed ? packed_idx_bits : 0u;
+        plan->packed = packed ? 1u : 0u;
+        // a packed word must hold tile | depth - bias | index; if this frame's depth range is too wide the host re-renders in pair mode
+        plan->packed_overflow = (packed && xf.total_bits + packed_idx_bits > 64u) ? 1u : 0u;
     }
 }
 
@@ -155,33 +168,46 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, Sor
 // one onesweep pass
 // ---------------------------------------------------------------------------------------------------
 
+// Sort modes. PAIRS: (u64 key, u32 value) in and out (standalone API, fallback). PACK: pairs in, single 64-bit words out
+// (first pass of a frame). PACKED: words in and out. A word is  tile << (depth_bits+idx_bits) | (depth-bias) << idx_bits | index:
+// the Gaussian index rides in the low bits of the key, so a pass moves 16 B per pair instead of 24 B, the value scatter
+// through shared memory disappears, and — pairs being emitted in ascending index order — sorting the bits above idx_bits
+// stably is exactly the reference's stable sort of (key, value) pairs.
+enum : int { MODE_PAIRS = 0, MODE_PACK = 1, MODE_PACKED = 2 };
+
+template <bool WITH_VALS>
 struct OnesweepSmem {
     uint64_t keys[SORT_TILE];
-    uint32_t vals[SORT_TILE];
-    uint32_t warp_hist[SORT_WARPS][SORT_BINS];
+    alignas(16) uint32_t warp_hist[SORT_WARPS][SORT_BINS];  // zeroed with 16-byte stores
     uint32_t global_base[SORT_BINS];
     uint32_t scan[SORT_BINS / 32];
     uint32_t part;
+    uint32_t vals[WITH_VALS ? SORT_TILE : 1];
 };
 static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phases");
 
-// One CTA = one tile of SORT_TILE pairs. Phases (6 block barriers):
-//   ticket + zero per-warp histograms | load keys (+values), early counts | per-bin: warp prefix, publish aggregate, bin scan |
-//   stable ranking (match.any) + key scatter to smem | look-back per bin | coalesced key write-out, value scatter | value write-out
-__global__ void __launch_bounds__(SORT_THREADS, TPDCU_SORT_MINB)
+__device__ __forceinline__ uint64_t pack_word(uint64_t key, uint32_t val, const KeyXform& x, uint32_t idx_bits) {
+    const uint32_t lo = (uint32_t)key - x.bias, hi = (uint32_t)(key >> 32);
+    const uint64_t packed = x.depth_bits >= 32u ? (((uint64_t)hi << 32) | lo) : (((uint64_t)hi << x.depth_bits) | lo);
+    return (packed << idx_bits) | val;
+}
+
+// One CTA = one tile of SORT_TILE pairs. Phases (block barriers in between):
+//   ticket + zero per-warp histograms | load keys, early counts | per-bin: warp prefix, publish aggregate, bin scan |
+//   stable ranking (match.any) + scatter to smem | look-back per bin | coalesced write-out (+ value scatter / write-out)
+template <int MODE>
+__global__ void __launch_bounds__(SORT_THREADS, MODE == MODE_PACKED ? TPDCU_SORT_MINB_PACKED : TPDCU_SORT_MINB)
 onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, FrameCtl* ctl,
                 const SortPlan* __restrict__ plan, uint32_t* lookback_pass, uint32_t pass) {
+    constexpr bool IN_PAIRS = MODE != MODE_PACKED, OUT_PAIRS = MODE == MODE_PAIRS;
+    using Smem = OnesweepSmem<OUT_PAIRS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    OnesweepSmem& sm = *reinterpret_cast<OnesweepSmem*>(smem_raw);
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     if (plan->skip[pass]) return;
     const uint32_t n = plan->n;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-#ifdef TPDCU_EXPERIMENT_BLOCKIDX_TICKET
-    if (tid == 0) sm.part = blockIdx.x;
-#else
     if (tid == 0) sm.part = atomicAdd(&ctl->sort_ticket[pass], 1u);
-#endif
     {
         uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[0][0]);
 #pragma unroll
@@ -199,13 +225,29 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     const uint32_t* __restrict__ src_vals = src ? vals1 : vals0;
     uint64_t* __restrict__ dst_keys = src ? keys0 : keys1;
     uint32_t* __restrict__ dst_vals = src ? vals0 : vals1;
+
+    // Tiles run in ticket order; the tile SORT_PREFETCH_TILES tickets ahead starts roughly when this one retires. One TMA
+    // bulk prefetch per array pulls it into L2 now, so that its loads are L2 hits then.
+    if (tid == 0) {
+        const uint64_t ahead = (uint64_t)(part + SORT_PREFETCH_TILES) * SORT_TILE;
+        if (ahead + SORT_TILE <= n) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_keys + ahead), "r"((uint32_t)(SORT_TILE * sizeof(uint64_t))) : "memory");
+            if (IN_PAIRS)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_vals + ahead), "r"((uint32_t)(SORT_TILE * sizeof(uint32_t))) : "memory");
+        }
+    }
     const KeyXform xf{ plan->bias, plan->depth_bits, plan->total_bits };
+    const uint32_t idx_bits = plan->idx_bits;
     const uint32_t shift = pass * SORT_RADIX_BITS, mask = pass_mask(pass, xf.total_bits);
+    // digit of an INPUT element / of an element as it sits in shared memory (= output format)
+    auto digit_in = [&](uint64_t k) { return IN_PAIRS ? digit_of(k, xf, shift, mask) : ((uint32_t)(k >> (idx_bits + shift)) & mask); };
+    auto digit_out = [&](uint64_t k) { return OUT_PAIRS ? digit_of(k, xf, shift, mask) : ((uint32_t)(k >> (idx_bits + shift)) & mask); };
 
     // ---- load (warp-striped: item k of lane l sits at warp_base + 32k + l) --------------------------
     uint64_t key[SORT_KPT];
     const uint32_t warp_base = tile_base + warp * (32u * SORT_KPT) + lane;
-    if (n_valid == SORT_TILE) {
+    const bool full = n_valid == SORT_TILE;
+    if (full) {
 #pragma unroll
         for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = src_keys[warp_base + k * 32u];
     } else {
@@ -221,8 +263,8 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
 #pragma unroll
         for (uint32_t r = 0; r < 4; ++r) {
             const uint32_t k = q * 4 + r;
-            const bool valid = n_valid == SORT_TILE || (warp_base + k * 32u) < n;
-            w |= (valid ? digit_of(key[k], xf, shift, mask) : mask) << (8u * r);
+            const bool valid = full || (warp_base + k * 32u) < n;
+            w |= (valid ? digit_in(key[k]) : mask) << (8u * r);
         }
         dpack[q] = w;
     }
@@ -231,6 +273,18 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     // ---- early counts: per-warp digit histograms ----------------------------------------------------
 #pragma unroll
     for (uint32_t k = 0; k < SORT_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_at(k)], 1u);
+
+    // values (pair input): issue the loads now, their latency hides behind the per-bin phases
+    uint32_t val[IN_PAIRS ? SORT_KPT : 1];
+    if (IN_PAIRS) {
+        if (full) {
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = src_vals[warp_base + k * 32u];
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = (warp_base + k * 32u) < n ? src_vals[warp_base + k * 32u] : 0u;
+        }
+    }
     __syncthreads();
 
     // ---- per-bin (thread == bin): exclusive prefix over warps, publish the tile aggregate, scan the bins -------------
@@ -260,8 +314,8 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     for (uint32_t w = 0; w < SORT_WARPS; ++w) sm.warp_hist[w][tid] += bin_base;
     __syncthreads();
 
-    // ---- stable ranking: peers with the same digit inside a 32-key row, rows in order; keys go straight to smem ------
-    uint32_t rank[SORT_KPT];
+    // ---- stable ranking: peers with the same digit inside a 32-key row, rows in order; elements go straight to smem ---
+    uint32_t rank[OUT_PAIRS ? SORT_KPT : 1];
 #pragma unroll
     for (uint32_t k = 0; k < SORT_KPT; ++k) {
         const uint32_t d = digit_at(k);
@@ -271,26 +325,17 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         __syncwarp();
         if (lower == 0) sm.warp_hist[warp][d] = base + __popc(peers);
         __syncwarp();
-        rank[k] = base + lower;
-        sm.keys[rank[k]] = key[k];
-    }
-
-    // values: issue the loads now, their latency hides behind the look-back
-    uint32_t val[SORT_KPT];
-    if (n_valid == SORT_TILE) {
-#pragma unroll
-        for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = src_vals[warp_base + k * 32u];
-    } else {
-#pragma unroll
-        for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = (warp_base + k * 32u) < n ? src_vals[warp_base + k * 32u] : 0u;
+        const uint32_t r = base + lower;
+        if (OUT_PAIRS) rank[k] = r;
+        sm.keys[r] = MODE == MODE_PACK ? pack_word(key[k], val[k], xf, idx_bits) : key[k];
     }
 
     // ---- decoupled look-back, one thread per bin -----------------------------------------------------
     {
         uint32_t excl = 0;
         if (part > 0) {
-            // Tiles in flight publish their aggregate long before their prefix, so the walk back to the nearest PREFIX can
-            // be hundreds of tiles deep right after launch: read LOOKBACK_BATCH descriptors per round trip, consume in order.
+            // Tiles in flight publish their aggregate well before their prefix, so the walk back to the nearest PREFIX is
+            // several tiles deep: read LOOKBACK_BATCH descriptors per round trip, consume them in order.
             int look = (int)part - 1;
             bool done = false;
             while (!done) {
@@ -302,13 +347,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
                 for (int j = 0; j < (int)LOOKBACK_BATCH; ++j) {
                     if (!done) {
                         uint32_t x = v[j];
-#ifdef TPDCU_EXPERIMENT_BLOCKIDX_TICKET
-                        for (uint32_t spins = 0; (x >> 30) == FLAG_INVALID && spins < (1u << 20); ++spins)
-                            x = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
-                        if ((x >> 30) == FLAG_INVALID) x = FLAG_PREFIX << 30;  // experiment-only safety valve: never hang
-#else
                         while ((x >> 30) == FLAG_INVALID) x = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
-#endif
                         excl += x & LOOKBACK_VALUE_MASK;
                         done = (x >> 30) == FLAG_PREFIX;  // tile 0 always carries a PREFIX, so look - j never goes below 0 unconsumed
                     }
@@ -322,23 +361,40 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     __syncthreads();
 
     // ---- write-out: position i of the locally sorted tile goes to global_base[digit] + i (contiguous per bin) ---------
-    uint32_t pos[SORT_KPT];
+    uint32_t pos[OUT_PAIRS ? SORT_KPT : 1];
 #pragma unroll
     for (uint32_t k = 0; k < SORT_KPT; ++k) {
         const uint32_t i = tid + k * SORT_THREADS;
         if (i < n_valid) {
             const uint64_t kk = sm.keys[i];
-            pos[k] = sm.global_base[digit_of(kk, xf, shift, mask)] + i;
-            dst_keys[pos[k]] = kk;
+            const uint32_t p = sm.global_base[digit_out(kk)] + i;
+            if (OUT_PAIRS) pos[k] = p;
+            dst_keys[p] = kk;
         }
     }
+    if (OUT_PAIRS) {
 #pragma unroll
-    for (uint32_t k = 0; k < SORT_KPT; ++k) sm.vals[rank[k]] = val[k];
-    __syncthreads();
+        for (uint32_t k = 0; k < SORT_KPT; ++k) sm.vals[rank[k]] = val[k];
+        __syncthreads();
 #pragma unroll
-    for (uint32_t k = 0; k < SORT_KPT; ++k) {
-        const uint32_t i = tid + k * SORT_THREADS;
-        if (i < n_valid) dst_vals[pos[k]] = sm.vals[i];
+        for (uint32_t k = 0; k < SORT_KPT; ++k) {
+            const uint32_t i = tid + k * SORT_THREADS;
+            if (i < n_valid) dst_vals[pos[k]] = sm.vals[i];
+        }
+    }
+}
+
+// introspection: packed words -> the reference's (key, value) arrays
+__global__ void sort_unpack_kernel(const uint64_t* keys0, const uint64_t* keys1, const SortPlan* plan, uint64_t* out_keys, uint32_t* out_vals) {
+    const uint64_t* w = plan->final_sel ? keys1 : keys0;
+    const uint32_t n = plan->n, ib = plan->idx_bits, db = plan->depth_bits, bias = plan->bias;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint64_t x = w[i];
+        const uint64_t kp = x >> ib;
+        const uint32_t depth = (db >= 32u ? (uint32_t)kp : (uint32_t)(kp & ((1ull << db) - 1ull))) + bias;
+        const uint32_t tile = db >= 32u ? (uint32_t)(kp >> 32) : (uint32_t)(kp >> db);
+        out_keys[i] = ((uint64_t)tile << 32) | depth;
+        out_vals[i] = (uint32_t)(x & ((1ull << ib) - 1ull));
     }
 }
 
@@ -355,17 +411,26 @@ __global__ void sort_copy_result_kernel(const uint64_t* keys1, const uint32_t* v
 
 uint32_t sort_parts(uint32_t capacity) { return (capacity + SORT_TILE - 1) / SORT_TILE; }
 
+template <int MODE>
+static cudaError_t set_smem_attr() {
+    return cudaFuncSetAttribute(onesweep_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(OnesweepSmem<MODE == MODE_PAIRS>));
+}
+
 cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cudaEvent_t ev_after_plan) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OnesweepSmem));
+        cudaError_t e = set_smem_attr<MODE_PAIRS>();
+        if (e == cudaSuccess) e = set_smem_attr<MODE_PACK>();
+        if (e == cudaSuccess) e = set_smem_attr<MODE_PACKED>();
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const uint32_t num_passes = (a.end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
     const uint32_t bound = n_host == UINT32_MAX ? a.capacity : n_host;
+    const uint32_t pib = a.packed_idx_bits;
     if (bound == 0 || num_passes == 0) {
-        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host == UINT32_MAX ? UINT32_MAX : 0u, a.capacity, 0, a.end_bit);
+        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host == UINT32_MAX ? UINT32_MAX : 0u, a.capacity, 0, a.end_bit, pib);
         if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
         return cudaGetLastError();
     }
@@ -374,14 +439,24 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     const uint32_t hist_max = (uint32_t)a.sm_count * 4u;
     if (hist_grid > hist_max) hist_grid = hist_max;
     sort_hist_kernel<<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.ctl, n_host, a.capacity, num_passes, a.end_bit);
-    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host, a.capacity, num_passes, a.end_bit);
+    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host, a.capacity, num_passes, a.end_bit, pib);
     if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
     const uint32_t parts = sort_parts(bound);
     const uint32_t parts_cap = sort_parts(a.capacity);
     for (uint32_t p = 0; p < num_passes; ++p) {
-        onesweep_kernel<<<parts, SORT_THREADS, sizeof(OnesweepSmem), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan,
-                                                                          a.lookback + (size_t)p * parts_cap * SORT_BINS, p);
+        uint32_t* lb = a.lookback + (size_t)p * parts_cap * SORT_BINS;
+        if (pib == 0)
+            onesweep_kernel<MODE_PAIRS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<true>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
+        else if (p == 0)
+            onesweep_kernel<MODE_PACK><<<parts, SORT_THREADS, sizeof(OnesweepSmem<false>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
+        else
+            onesweep_kernel<MODE_PACKED><<<parts, SORT_THREADS, sizeof(OnesweepSmem<false>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sort_unpack(const SortLaunch& a, uint64_t* out_keys, uint32_t* out_vals, cudaStream_t s) {
+    sort_unpack_kernel<<<(uint32_t)a.sm_count * 8u, 256, 0, s>>>(a.keys[0], a.keys[1], a.plan, out_keys, out_vals);
     return cudaGetLastError();
 }
 

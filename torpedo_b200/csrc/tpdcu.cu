@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -38,9 +39,10 @@ static int fail(int code, const std::string& msg) {
 struct FrameStatus {  // pinned host mirror of what a frame reports back
     uint32_t pairs_total;
     uint32_t visible;
-    uint32_t passes_run;
-    uint32_t pad;
+    // head of the SortPlan as the frame left it
+    uint32_t n, num_passes, final_sel, passes_run, bias, depth_bits, total_bits, idx_bits, packed, packed_overflow;
 };
+static_assert(offsetof(SortPlan, packed_overflow) == 9 * sizeof(uint32_t), "FrameStatus mirrors the head of SortPlan");
 
 struct tpdcu_ctx {
     int device = 0;
@@ -74,6 +76,7 @@ struct tpdcu_ctx {
     uint32_t capacity = 0;
     uint64_t* keys[2] = { nullptr, nullptr };
     uint32_t* vals[2] = { nullptr, nullptr };
+    bool packed_disabled = false;  // a frame whose depth range did not fit packed sort words switches the context to pair mode
     bool keep_unsorted = false;
     uint64_t* unsorted_keys = nullptr;
     uint32_t* unsorted_vals = nullptr;
@@ -119,6 +122,14 @@ static uint32_t frame_end_bit(const tpdcu_ctx* c) {
     return 32u + (tiles > 1 ? bit_length(tiles - 1) : 0u);
 }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// Packed sort words hold tile | depth - bias | index (sort.cu). Used when the index and tile bits leave at least 24 bits for
+// the depth range of a frame (27 bits cover the default near/far planes); verified per frame on the device.
+static uint32_t packed_idx_bits(const tpdcu_ctx* c) {
+    if (c->packed_disabled || c->n == 0) return 0;
+    const uint32_t idx_bits = std::max(1u, bit_length(c->n - 1));
+    const uint32_t tile_bits = frame_end_bit(c) - 32u;
+    return (idx_bits + tile_bits <= 40u) ? idx_bits : 0u;
+}
 
 static void free_scene(tpdcu_ctx* c) {
     cudaFree(c->posop); cudaFree(c->cov_a); cudaFree(c->cov_b); cudaFree(c->sh); cudaFree(c->entity);
@@ -234,6 +245,7 @@ static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cud
     so.ctl = ctl; so.plan = c->plan;
     so.lookback = reinterpret_cast<uint32_t*>(c->zero_region + c->off_lookback);
     so.capacity = c->capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
+    so.packed_idx_bits = packed_idx_bits(c);
     CK(launch_sort(so, UINT32_MAX, s, t ? c->ev[3] : nullptr));
     if (t) CK(cudaEventRecord(c->ev[4], s));
 
@@ -248,7 +260,21 @@ static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cud
     if (t) CK(cudaEventRecord(c->ev[6], s));
 
     CK(cudaMemcpyAsync(&c->status[slot].pairs_total, &ctl->pairs_total, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&c->status[slot].passes_run, &c->plan->passes_run, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&c->status[slot].n, c->plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    return TPDCU_OK;
+}
+
+// Does a finished frame have to be rendered again (buffers too small / packed words too narrow)? Adjusts the context.
+static int frame_needs_rerender(tpdcu_ctx* c, const FrameStatus& st, bool* again) {
+    *again = false;
+    if (st.pairs_total > c->capacity) {
+        *again = true;
+        return TPDCU_OK;
+    }
+    if (st.packed_overflow) {
+        c->packed_disabled = true;
+        *again = true;
+    }
     return TPDCU_OK;
 }
 
@@ -274,10 +300,13 @@ static int finish_internal(tpdcu_ctx* c) {
     for (int attempt = 0; c->frame_pending; ++attempt) {
         CK(cudaEventSynchronize(c->frame_done));
         const uint32_t pairs = c->status[0].pairs_total;
-        if (pairs <= c->capacity) { c->frame_pending = false; c->frame_valid = true; break; }
-        if (attempt >= 3) return fail(TPDCU_ERR_STATE, "pair buffer kept overflowing");
+        bool again = false;
+        if (int r = frame_needs_rerender(c, c->status[0], &again)) return r;
+        if (!again) { c->frame_pending = false; c->frame_valid = true; break; }
+        if (attempt >= 4) return fail(TPDCU_ERR_STATE, "pair buffer kept overflowing");
         CK(cudaStreamSynchronize(c->last_stream));
-        if (int r = ensure_pairs(c, grown_capacity(pairs))) return r;
+        if (pairs > c->capacity)
+            if (int r = ensure_pairs(c, grown_capacity(pairs))) return r;
         size_t pitch; uint8_t* out = out_ptr(c, &pitch);
         if (int r = enqueue_frame(c, c->last_ubo, c->last_sh_degree, c->last_stream, out, pitch, 0)) return r;
         CK(cudaEventRecord(c->frame_done, c->last_stream));
@@ -528,7 +557,7 @@ int tpdcu_raster_views(tpdcu_ctx* c, const float* camera_ubos, uint32_t n_views,
     c->timing = false;  // per-stage events describe single frames only
     int rc = TPDCU_OK;
     for (int attempt = 0; !todo.empty() && rc == TPDCU_OK; ++attempt) {
-        if (attempt >= 4) { rc = fail(TPDCU_ERR_STATE, "pair buffer kept overflowing"); break; }
+        if (attempt >= 5) { rc = fail(TPDCU_ERR_STATE, "pair buffer kept overflowing"); break; }
         for (uint32_t v : todo) {
             rc = enqueue_frame(c, camera_ubos + (size_t)v * TPDCU_CAMERA_FLOATS, sh_degree, s,
                                reinterpret_cast<uint8_t*>(d_frames) + (size_t)v * frame_stride_bytes, pitch, v);
@@ -539,9 +568,12 @@ int tpdcu_raster_views(tpdcu_ctx* c, const float* camera_ubos, uint32_t n_views,
         if (e != cudaSuccess) { rc = fail(TPDCU_ERR_CUDA, std::string("batch sync: ") + cudaGetErrorString(e)); break; }
         std::vector<uint32_t> again;
         uint32_t max_pairs = 0;
-        for (uint32_t v : todo)
-            if (c->status[v].pairs_total > c->capacity) { again.push_back(v); max_pairs = std::max(max_pairs, c->status[v].pairs_total); }
-        if (!again.empty()) rc = ensure_pairs(c, grown_capacity(max_pairs));
+        for (uint32_t v : todo) {
+            bool redo = false;
+            frame_needs_rerender(c, c->status[v], &redo);
+            if (redo) { again.push_back(v); max_pairs = std::max(max_pairs, c->status[v].pairs_total); }
+        }
+        if (!again.empty() && max_pairs > c->capacity) rc = ensure_pairs(c, grown_capacity(max_pairs));
         todo.swap(again);
     }
     c->timing = timing;
@@ -601,10 +633,20 @@ static int read_sorted(tpdcu_ctx* c, void* host, uint32_t count, bool want_keys)
     if (int r = finish_internal(c)) return r;
     if (count > c->status[0].pairs_total) return fail(TPDCU_ERR_INVALID, "count exceeds the frame's pair count");
     if (count == 0) return TPDCU_OK;
-    SortPlan plan;
-    CK(cudaMemcpyAsync(&plan, c->plan, sizeof(plan), cudaMemcpyDeviceToHost, c->last_stream));
-    CK(cudaStreamSynchronize(c->last_stream));
-    const void* src = want_keys ? (const void*)c->keys[plan.final_sel & 1] : (const void*)c->vals[plan.final_sel & 1];
+    const FrameStatus& st = c->status[0];
+    const void* src;
+    if (st.packed) {
+        // the frame's result is one array of packed words: expand it into the reference's (key, value) arrays in the
+        // buffers the sort no longer needs
+        SortLaunch so{};
+        so.keys[0] = c->keys[0]; so.keys[1] = c->keys[1]; so.plan = c->plan; so.sm_count = c->sm_count;
+        uint64_t* uk = c->keys[(st.final_sel & 1u) ^ 1u];
+        uint32_t* uv = c->vals[1];
+        CK(launch_sort_unpack(so, uk, uv, c->last_stream));
+        src = want_keys ? (const void*)uk : (const void*)uv;
+    } else {
+        src = want_keys ? (const void*)c->keys[st.final_sel & 1u] : (const void*)c->vals[st.final_sel & 1u];
+    }
     CK(cudaMemcpyAsync(host, src, (size_t)count * (want_keys ? 8 : 4), cudaMemcpyDeviceToHost, c->last_stream));
     CK(cudaStreamSynchronize(c->last_stream));
     return TPDCU_OK;
@@ -697,7 +739,7 @@ int tpdcu_sort_pairs_device(tpdcu_ctx* c, uint64_t* d_keys, uint32_t* d_vals, ui
     CK(launch_sort(so, n, s, nullptr));
     CK(cudaEventRecord(c->sort_ev[1], s));
     CK(launch_sort_copy_result(so, d_keys, d_vals, n, s));
-    CK(cudaMemcpyAsync(&c->status[0].passes_run, &c->plan->passes_run, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&c->status[0].n, c->plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     c->last_stream = s;
     return TPDCU_OK;
 }
