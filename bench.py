@@ -283,6 +283,7 @@ def run_gpu(args):
     eng.enable_stage_timing(False)
     stages = {k: statistics.median(r[0][k] for r in stage_runs) for k in stage_runs[0][0]}
     stage_pairs = statistics.median(r[1] for r in stage_runs)
+    sort_info = eng.sort_info()
 
     # ---- end-to-end through the public API with host buffers (rank-local; max over ranks) -----------------------------
     host = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.uint8).pin_memory()
@@ -313,7 +314,10 @@ def run_gpu(args):
         peak, peak_src = measured_peak_hbm()
         passes = max(int(stages["passes_run"]), 1)
         pass_ms = stages["sort_passes"] / passes
-        alg_bytes = stage_pairs * 24.0                     # one 8-byte key + 4-byte value read and written per pass
+        if sort_info["packed"]:   # single 64-bit words: 8 B in + 8 B out per pass; the first pass reads (key, value) pairs: 12 B in
+            alg_bytes = stage_pairs * (20.0 + 16.0 * (passes - 1)) / passes
+        else:                     # (u64 key, u32 value) pairs: 12 B in + 12 B out per pass
+            alg_bytes = stage_pairs * 24.0
         achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
         sort_ms = stages["sort_hist"] + stages["sort_passes"]
         line = {
@@ -327,13 +331,16 @@ def run_gpu(args):
             "pairs": int(stage_pairs), "visible": int(visible), "capacity_ok": bool(cap_ok),
             "stages_ms": stages,
             "sort_gkeys_per_s": stage_pairs / (sort_ms * 1e-3) / 1e9 if sort_ms > 0 else None,
-            "roofline": {"kernel": "onesweep_kernel (one 8-bit digit pass over (u64 key, u32 value) pairs)", "bound": "hbm",
+            "sort": dict(sort_info, passes_run=passes, bytes_per_pair=(8 + 20 + 16 * (passes - 1)) if sort_info["packed"] else (8 + 24 * passes)),
+            "roofline": {"kernel": "onesweep_kernel (one 8-bit digit pass of the tile|depth|index sort; average over the passes of a frame)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": ncu_traffic_per_launch(), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pass_ms,
                          "peak_source": peak_src},
             "e2e": {"value": e2e_ms / e2e_steps, "unit": "ms/frame", "h2d_bytes_per_step": 136, "d2h_bytes_per_step": frame_bytes,
                     "steps": e2e_steps, "checksum": checksum},
-            "gpu_launches": K * (6 + passes),   # setup, preprocess, hist, plan, ranges, blend + one onesweep launch per pass that ran
+            # per frame: setup, preprocess (geometry+scan+duplication), colour, histogram, plan, ranges, blend + one onesweep
+            # launch per 8-bit digit of the widest possible key (a pass whose digit is constant still launches and exits)
+            "gpu_launches": K * (7 + (32 + ((WIDTH + 15) // 16 * ((HEIGHT + 15) // 16) - 1).bit_length() + 7) // 8),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

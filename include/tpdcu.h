@@ -121,6 +121,13 @@ int tpdcu_read_unsorted(tpdcu_ctx* ctx, uint64_t* host_keys, uint32_t* host_vals
  * [4] ranges [5] blend [6] whole frame [7] number of onesweep passes that actually ran. */
 int tpdcu_enable_stage_timing(tpdcu_ctx* ctx, int enable);
 int tpdcu_stage_times_ms(tpdcu_ctx* ctx, float times_ms[TPDCU_NUM_STAGES]);
+/* How the last finished frame was sorted. packed = 1: single 64-bit words  tile | depth - bias | index  (16 B moved per
+ * pair and pass; the first pass reads pairs: 20 B), packed = 0: (u64 key, u32 value) pairs (24 B per pair and pass).
+ * depth_bits / idx_bits / total_bits: widths of the depth-minus-bias field, the index field and the sorted bit range. */
+int tpdcu_get_sort_info(tpdcu_ctx* ctx, uint32_t* packed, uint32_t* depth_bits, uint32_t* idx_bits, uint32_t* total_bits);
+/* Testing aid: pretend packed sort words are only `bits` wide (default 64). A frame whose tile|depth|index does not fit is
+ * detected on the device and re-rendered in pair mode; this knob lets the tests exercise that path on small scenes. */
+int tpdcu_set_packed_word_bits(tpdcu_ctx* ctx, uint32_t bits);
 /* Current pair-buffer capacity (grow-only, like GaussianEngine::reallocateBuffers :793-804) */
 int tpdcu_get_capacity(tpdcu_ctx* ctx, uint32_t* capacity_pairs);
 int tpdcu_reserve_pairs(tpdcu_ctx* ctx, uint32_t capacity_pairs);

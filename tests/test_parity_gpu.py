@@ -243,3 +243,31 @@ def test_raster_views_batch(E, oracle):
         ref = oracle.render(g, ubos[k], w, h, 3)
         assert np.abs(out[k].astype(np.int32) - ref.rgba.astype(np.int32)).max() <= 1, k
     eng.close()
+
+
+def test_packed_sort_words_and_pair_mode_fallback(E, oracle):
+    """Frames are sorted as single 64-bit words (tile | depth - min | index) when they fit; a frame that does not fit is
+    detected on the device and re-rendered in (key, value) pair mode. Both give the reference's stable order bit for bit."""
+    from torpedo_b200 import scenes
+    _, cams = golden_cameras()
+    g = scenes.garden(20000, seed=71, log_scale_mean=-3.6)
+    ref = oracle.render(g, cams["garden_256x144"], 256, 144, 3)
+    scene = E.Scene()
+    scene.add_group(g)
+    eng = E.GaussianEngine(256, 144)
+    eng.compile(scene)
+    eng.keep_unsorted(True)
+    eng.raster_ubo(cams["garden_256x144"], 3)
+    img = eng.draw()
+    info = eng.sort_info()
+    assert info["packed"] and info["idx_bits"] == 15 and info["total_bits"] == info["depth_bits"] + 8
+    assert info["total_bits"] + info["idx_bits"] <= 64
+    assert_frame_parity(eng, img, ref, len(g))
+    # now pretend the word is too narrow for this frame: device-side detection, re-render in pair mode, same results
+    eng.set_packed_word_bits(info["total_bits"] + info["idx_bits"] - 1)
+    eng.raster_ubo(cams["garden_256x144"], 3)
+    img2 = eng.draw()
+    assert not eng.sort_info()["packed"]
+    assert_frame_parity(eng, img2, ref, len(g))
+    assert (img2 == img).all()
+    eng.close()

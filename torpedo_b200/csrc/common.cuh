@@ -157,6 +157,7 @@ struct SortLaunch {
     uint32_t capacity;                    // launch bound for grids
     uint32_t end_bit;                     // 32 + tile bits (frame path) or the caller's end bit (standalone)
     uint32_t packed_idx_bits;             // 0: pair mode; else bits reserved for the Gaussian index in packed words
+    uint32_t packed_word_bits;            // 64 (testing aid: smaller values force the overflow -> pair-mode fallback)
     int sm_count;
 };
 // n is taken from ctl->pairs_total clamped to capacity (frame path) when n_host == UINT32_MAX,

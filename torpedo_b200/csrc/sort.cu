@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
 // ---------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, SortPlan* plan, uint32_t n_host, uint32_t capacity,
-                                                               uint32_t num_passes, uint32_t end_bit, uint32_t packed_idx_bits) {
+                                                               uint32_t num_passes, uint32_t end_bit, uint32_t packed_idx_bits, uint32_t packed_word_bits) {
     __shared__ uint32_t s_warp[SORT_BINS / 32];
     __shared__ uint32_t s_skip[SORT_MAX_PASSES];
     const uint32_t n = n_host == UINT32_MAX ? min(ctl->pairs_total, capacity) : n_host;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, Sor
         plan->idx_bits = packed ? packed_idx_bits : 0u;
         plan->packed = packed ? 1u : 0u;
         // a packed word must hold tile | depth - bias | index; if this frame's depth range is too wide the host re-renders in pair mode
-        plan->packed_overflow = (packed && xf.total_bits + packed_idx_bits > 64u) ? 1u : 0u;
+        plan->packed_overflow = (packed && xf.total_bits + packed_idx_bits > packed_word_bits) ? 1u : 0u;
     }
 }
 
@@ -430,7 +430,7 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     const uint32_t bound = n_host == UINT32_MAX ? a.capacity : n_host;
     const uint32_t pib = a.packed_idx_bits;
     if (bound == 0 || num_passes == 0) {
-        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host == UINT32_MAX ? UINT32_MAX : 0u, a.capacity, 0, a.end_bit, pib);
+        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host == UINT32_MAX ? UINT32_MAX : 0u, a.capacity, 0, a.end_bit, pib, a.packed_word_bits ? a.packed_word_bits : 64u);
         if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
         return cudaGetLastError();
     }
@@ -439,7 +439,7 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     const uint32_t hist_max = (uint32_t)a.sm_count * 4u;
     if (hist_grid > hist_max) hist_grid = hist_max;
     sort_hist_kernel<<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.ctl, n_host, a.capacity, num_passes, a.end_bit);
-    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host, a.capacity, num_passes, a.end_bit, pib);
+    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host, a.capacity, num_passes, a.end_bit, pib, a.packed_word_bits ? a.packed_word_bits : 64u);
     if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
     const uint32_t parts = sort_parts(bound);
     const uint32_t parts_cap = sort_parts(a.capacity);

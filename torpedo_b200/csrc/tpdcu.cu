@@ -76,6 +76,7 @@ struct tpdcu_ctx {
     uint32_t capacity = 0;
     uint64_t* keys[2] = { nullptr, nullptr };
     uint32_t* vals[2] = { nullptr, nullptr };
+    uint32_t packed_word_bits = 64;
     bool packed_disabled = false;  // a frame whose depth range did not fit packed sort words switches the context to pair mode
     bool keep_unsorted = false;
     uint64_t* unsorted_keys = nullptr;
@@ -246,6 +247,7 @@ static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cud
     so.lookback = reinterpret_cast<uint32_t*>(c->zero_region + c->off_lookback);
     so.capacity = c->capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
     so.packed_idx_bits = packed_idx_bits(c);
+    so.packed_word_bits = c->packed_word_bits;
     CK(launch_sort(so, UINT32_MAX, s, t ? c->ev[3] : nullptr));
     if (t) CK(cudaEventRecord(c->ev[4], s));
 
@@ -694,6 +696,24 @@ int tpdcu_stage_times_ms(tpdcu_ctx* c, float times_ms[TPDCU_NUM_STAGES]) {
     if (int r = finish_internal(c)) return r;
     // stage_ms[k] = ev[k+1]-ev[k]: 0 clear+setup | 1 preprocess | 2 hist+plan | 3 passes | 4 ranges | 5 blend
     memcpy(times_ms, c->stage_ms, sizeof(float) * TPDCU_NUM_STAGES);
+    return TPDCU_OK;
+}
+
+int tpdcu_get_sort_info(tpdcu_ctx* c, uint32_t* packed, uint32_t* depth_bits, uint32_t* idx_bits, uint32_t* total_bits) {
+    if (int r = check_ready(c)) return r;
+    if (int r = finish_internal(c)) return r;
+    const FrameStatus& st = c->status[0];
+    if (packed) *packed = st.packed;
+    if (depth_bits) *depth_bits = st.depth_bits;
+    if (idx_bits) *idx_bits = st.idx_bits;
+    if (total_bits) *total_bits = st.total_bits;
+    return TPDCU_OK;
+}
+
+int tpdcu_set_packed_word_bits(tpdcu_ctx* c, uint32_t bits) {
+    if (int r = check_ready(c)) return r;
+    if (bits < 1 || bits > 64) return fail(TPDCU_ERR_INVALID, "bits must be in [1, 64]");
+    c->packed_word_bits = bits;
     return TPDCU_OK;
 }
 

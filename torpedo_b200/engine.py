@@ -292,6 +292,14 @@ class GaussianEngine:
         names = ["setup", "preprocess", "sort_hist", "sort_passes", "ranges", "blend", "frame", "passes_run"]
         return dict(zip(names, [float(x) for x in t]))
 
+    def sort_info(self) -> dict:
+        p, d, i, t = u32(0), u32(0), u32(0), u32(0)
+        check(tpdcu().tpdcu_get_sort_info(self._ctx, C.byref(p), C.byref(d), C.byref(i), C.byref(t)))
+        return {"packed": bool(p.value), "depth_bits": d.value, "idx_bits": i.value, "total_bits": t.value}
+
+    def set_packed_word_bits(self, bits: int) -> None:
+        check(tpdcu().tpdcu_set_packed_word_bits(self._ctx, bits))
+
     def capacity(self) -> int:
         c = u32(0)
         check(tpdcu().tpdcu_get_capacity(self._ctx, C.byref(c)))
