@@ -271,3 +271,22 @@ def test_packed_sort_words_and_pair_mode_fallback(E, oracle):
     assert_frame_parity(eng, img2, ref, len(g))
     assert (img2 == img).all()
     eng.close()
+
+
+def test_cpp_hello_gaussian_demo(E, oracle, built_libs):
+    """The reference's HelloGaussian demo compiled against the header-only C++ drop-in gives the same frame as the oracle."""
+    import os
+    import subprocess
+    from torpedo_b200 import scenes
+    exe = os.path.join(built_libs.LIB_DIR, "hello_gaussian")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    words = out.stdout.split()
+    pairs, visible, checksum = int(words[1]), int(words[3]), int(words[5])
+    cam = E.PerspectiveCamera(1280, 720)
+    cam.look_at(E.to_cartesian(0.785, 0.9, 8.0), (0, 0, 0), (0, 0, 1))
+    g = scenes.hello_gaussian(8192, seed=1)
+    ref = oracle.render(g, cam.pack(), 1280, 720, 0, entity_idx=np.r_[np.zeros(8192, np.uint32), np.uint32(1)],
+                        models=np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (2, 1)))
+    assert pairs == ref.pairs and visible == int((ref.tiles > 0).sum())
+    assert abs(checksum - int(ref.rgba[..., :3].astype(np.int64).sum())) <= 1280 * 720 * 3 * 0.001
