@@ -84,9 +84,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+struct BlendEntry {
+    float4 g0;  // px, py, A', B'
+    float4 g1;  // C', opacity, power2 threshold, -
+};
 struct BlendSmem {
-    float4 g0[BLEND_QUEUE];                      // px, py, A', B'
-    float4 g1[BLEND_QUEUE];                      // C', opacity, power2 threshold, -
+    BlendEntry ent[BLEND_QUEUE];
     float4 col[BLEND_QUEUE];                     // r, g, b
     uint16_t list[BLEND_WARPS][BLEND_QUEUE];     // per-quadrant queue entry indices, in sorted order
     uint32_t cnt[BLEND_WARPS][BLEND_WARPS + 1];  // [staging warp][tile, quadrant 0..3] survivors of the current round
@@ -101,7 +104,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // quadrant `warp`: origin (8*(warp&1), 8*(warp>>1)); lane -> pixel pair at (2*(lane&3), lane>>2) inside it
     const uint32_t x0 = tile_x0 + 8u * (warp & 1u) + 2u * (lane & 3u), y0 = tile_y0 + 8u * (warp >> 1) + (lane >> 2);
-    const float fx0 = (float)x0, fy0 = (float)y0;
+    float fx0 = (float)x0, fy0 = (float)y0;
+    asm volatile("" : "+f"(fx0), "+f"(fy0));  // keep the pixel coordinates in registers: do not re-convert them per splat
     const float tile_fx0 = (float)tile_x0, tile_fy0 = (float)tile_y0;
 
     if (a.plan->packed_overflow) return;  // this frame is going to be re-rendered in pair mode
@@ -164,8 +168,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
             if (keep) {
                 const uint32_t pos = qn + before[0] + __popc(ballot[0] & lanemask_lt());
                 const float4 col = __ldg(a.color + g);
-                sm.g0[pos] = make_float4(ra.x, ra.y, (-0.5f * LOG2E) * ra.z, -LOG2E * ra.w);
-                sm.g1[pos] = make_float4((-0.5f * LOG2E) * rb.x, rb.y, -__log2f(255.0f * rb.y) - 0.01f, 0.0f);
+                sm.ent[pos].g0 = make_float4(ra.x, ra.y, (-0.5f * LOG2E) * ra.z, -LOG2E * ra.w);
+                sm.ent[pos].g1 = make_float4((-0.5f * LOG2E) * rb.x, rb.y, -__log2f(255.0f * rb.y) - 0.01f, 0.0f);
                 sm.col[pos] = col;
 #pragma unroll
                 for (uint32_t q = 0; q < BLEND_WARPS; ++q)
@@ -184,8 +188,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
         for (uint32_t j = 0; j < my_ln; ++j) {
             if ((j & 7u) == 0u && __all_sync(0xffffffffu, live == 0)) break;  // the whole quadrant is done (uniform branch)
             const uint32_t e = my_list[j];
-            const float4 q0 = sm.g0[e];
-            const float4 q1 = sm.g1[e];
+            const float4 q0 = sm.ent[e].g0;
+            const float4 q1 = sm.ent[e].g1;
             const float dx0 = q0.x - fx0, dy = q0.y - fy0;
             const float dx1 = dx0 - 1.0f;
             const float by = q0.w * dy;

@@ -45,6 +45,12 @@ __device__ __forceinline__ uint32_t digit_of(uint64_t key, const KeyXform& x, ui
     const uint64_t packed = x.depth_bits >= 32u ? (((uint64_t)hi << 32) | lo) : (((uint64_t)hi << x.depth_bits) | lo);
     return (uint32_t)(packed >> shift) & mask;
 }
+__device__ __forceinline__ uint64_t pack_word(uint64_t key, uint32_t val, const KeyXform& x, uint32_t idx_bits) {
+    const uint32_t lo = (uint32_t)key - x.bias, hi = (uint32_t)(key >> 32);
+    const uint64_t packed = x.depth_bits >= 32u ? (((uint64_t)hi << 32) | lo) : (((uint64_t)hi << x.depth_bits) | lo);
+    return (packed << idx_bits) | val;
+}
+
 __device__ __forceinline__ uint32_t pass_mask(uint32_t pass, uint32_t total_bits) {
     const uint32_t left = total_bits > pass * SORT_RADIX_BITS ? total_bits - pass * SORT_RADIX_BITS : 0u;
     return left >= SORT_RADIX_BITS ? (SORT_BINS - 1u) : ((1u << left) - 1u);
@@ -84,13 +90,15 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
         }
         const uint32_t valid = first >= n ? 0u : min(HIST_KPT, n - first);
         if (valid) {
+#pragma unroll
+            for (uint32_t j = 0; j < HIST_KPT; ++j) k[j] = pack_word(k[j], 0u, xf, 0u);  // tile << depth_bits | depth - bias, once per key
             for (uint32_t p = 0; p < num_passes; ++p) {
                 const uint32_t shift = p * SORT_RADIX_BITS, mask = pass_mask(p, xf.total_bits);
-                uint32_t run_digit = digit_of(k[0], xf, shift, mask), run = 1;
+                uint32_t run_digit = (uint32_t)(k[0] >> shift) & mask, run = 1;
 #pragma unroll
                 for (uint32_t j = 1; j < HIST_KPT; ++j) {
                     if (j < valid) {
-                        const uint32_t d = digit_of(k[j], xf, shift, mask);
+                        const uint32_t d = (uint32_t)(k[j] >> shift) & mask;
                         if (d != run_digit) {
                             atomicAdd(&h[p][run_digit], run);
                             run_digit = d;
@@ -185,12 +193,6 @@ struct OnesweepSmem {
     uint32_t vals[WITH_VALS ? SORT_TILE : 1];
 };
 static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phases");
-
-__device__ __forceinline__ uint64_t pack_word(uint64_t key, uint32_t val, const KeyXform& x, uint32_t idx_bits) {
-    const uint32_t lo = (uint32_t)key - x.bias, hi = (uint32_t)(key >> 32);
-    const uint64_t packed = x.depth_bits >= 32u ? (((uint64_t)hi << 32) | lo) : (((uint64_t)hi << x.depth_bits) | lo);
-    return (packed << idx_bits) | val;
-}
 
 // One CTA = one tile of SORT_TILE pairs. Phases (block barriers in between):
 //   ticket + zero per-warp histograms | load keys, early counts | per-bin: warp prefix, publish aggregate, bin scan |
