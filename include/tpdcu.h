@@ -128,6 +128,10 @@ int tpdcu_get_sort_info(tpdcu_ctx* ctx, uint32_t* packed, uint32_t* depth_bits, 
 /* Testing aid: pretend packed sort words are only `bits` wide (default 64). A frame whose tile|depth|index does not fit is
  * detected on the device and re-rendered in pair mode; this knob lets the tests exercise that path on small scenes. */
 int tpdcu_set_packed_word_bits(tpdcu_ctx* ctx, uint32_t bits);
+/* The frame's launches between the camera setup and the blend do not change from frame to frame; they are captured once
+ * into a CUDA graph and replayed (the reference re-records two command buffers every frame, GaussianEngine.cpp:637-697).
+ * enable: 1/0 to switch replay on/off, -1 to only query. captures/launches (nullable): counters since tpdcu_create. */
+int tpdcu_set_graph_replay(tpdcu_ctx* ctx, int enable, uint32_t* captures, uint32_t* launches);
 /* Current pair-buffer capacity (grow-only, like GaussianEngine::reallocateBuffers :793-804) */
 int tpdcu_get_capacity(tpdcu_ctx* ctx, uint32_t* capacity_pairs);
 int tpdcu_reserve_pairs(tpdcu_ctx* ctx, uint32_t capacity_pairs);

@@ -164,6 +164,7 @@ struct SortLaunch {
 // else from n_host (standalone sort).
 cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cudaEvent_t ev_after_plan);
 uint32_t sort_parts(uint32_t capacity);
+cudaError_t init_sort_attributes();
 
 struct RasterLaunch {
     const uint64_t* keys[2];

@@ -419,15 +419,15 @@ static cudaError_t set_smem_attr() {
                                 (int)sizeof(OnesweepSmem<MODE == MODE_PAIRS>));
 }
 
+// opt in to > 48 KB of dynamic shared memory; called once per context, outside any stream capture
+cudaError_t init_sort_attributes() {
+    cudaError_t e = set_smem_attr<MODE_PAIRS>();
+    if (e == cudaSuccess) e = set_smem_attr<MODE_PACK>();
+    if (e == cudaSuccess) e = set_smem_attr<MODE_PACKED>();
+    return e;
+}
+
 cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cudaEvent_t ev_after_plan) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = set_smem_attr<MODE_PAIRS>();
-        if (e == cudaSuccess) e = set_smem_attr<MODE_PACK>();
-        if (e == cudaSuccess) e = set_smem_attr<MODE_PACKED>();
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     const uint32_t num_passes = (a.end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
     const uint32_t bound = n_host == UINT32_MAX ? a.capacity : n_host;
     const uint32_t pib = a.packed_idx_bits;

@@ -104,6 +104,20 @@ struct tpdcu_ctx {
     cudaEvent_t ev[7] = {};
     float stage_ms[TPDCU_NUM_STAGES] = {};
 
+    // CUDA graph of the frame's parameter-invariant middle section (memset .. ranges); re-captured when anything it bakes in changes
+    struct GraphSig {
+        const void* zero_region; size_t zero_bytes; const void* keys0; const void* keys1; const void* geo; const void* posop;
+        uint32_t n, capacity, width, height, sh_degree, packed_idx_bits, packed_word_bits, entity_count;
+        bool keep_unsorted;
+        bool operator==(const GraphSig& o) const { return memcmp(this, &o, sizeof(GraphSig)) == 0; }
+    };
+    bool use_graph = true;
+    bool graph_valid = false;
+    GraphSig graph_sig{};
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t capture_stream = nullptr;
+    uint32_t graph_launches = 0, graph_captures = 0;
+
     // standalone sort
     cudaEvent_t sort_ev[2] = {};
     float sort_ms = 0.f;
@@ -198,6 +212,37 @@ static int ensure_target(tpdcu_ctx* c) {
     return TPDCU_OK;
 }
 
+struct FrameLaunch {
+    PreprocessLaunch pre;
+    SortLaunch sort;
+    RasterLaunch raster;
+};
+
+// The part of a frame whose launch parameters do not change from frame to frame: everything between the camera setup and
+// the blend. Either enqueued directly or captured once into a CUDA graph and replayed (13 launches -> 1 graph launch).
+static int enqueue_middle(tpdcu_ctx* c, const FrameLaunch& f, cudaStream_t s, bool timing) {
+    CK(cudaMemsetAsync(c->zero_region, 0, c->zero_bytes, s));
+    if (timing) CK(cudaEventRecord(c->ev[1], s));
+    CK(launch_preprocess(f.pre, s));
+    CK(launch_color(f.pre, s));
+    if (c->keep_unsorted && c->capacity) {
+        CK(cudaMemcpyAsync(c->unsorted_keys, c->keys[0], (size_t)c->capacity * 8, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(c->unsorted_vals, c->vals[0], (size_t)c->capacity * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    if (timing) CK(cudaEventRecord(c->ev[2], s));
+    CK(launch_sort(f.sort, UINT32_MAX, s, timing ? c->ev[3] : nullptr));
+    if (timing) CK(cudaEventRecord(c->ev[4], s));
+    CK(launch_ranges(f.raster, s));
+    if (timing) CK(cudaEventRecord(c->ev[5], s));
+    return TPDCU_OK;
+}
+
+static void drop_graph(tpdcu_ctx* c) {
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    c->graph_exec = nullptr;
+    c->graph_valid = false;
+}
+
 // Enqueue one frame. No host synchronisation.
 static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cudaStream_t s, uint8_t* out, size_t pitch,
                          uint32_t slot) {
@@ -208,12 +253,18 @@ static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cud
         CK(cudaMemcpyAsync(c->models, c->models_host.data(), sizeof(float) * 16 * c->entity_count, cudaMemcpyHostToDevice, s));
         c->models_dirty = false;
     }
+    if (c->keep_unsorted && c->capacity && c->unsorted_capacity < c->capacity) {
+        cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
+        c->unsorted_keys = nullptr; c->unsorted_vals = nullptr; c->unsorted_capacity = 0;
+        CK(cudaMalloc(&c->unsorted_keys, (size_t)c->capacity * 8));
+        CK(cudaMalloc(&c->unsorted_vals, (size_t)c->capacity * 4));
+        c->unsorted_capacity = c->capacity;
+    }
     const bool t = c->timing;
-    if (t) CK(cudaEventRecord(c->ev[0], s));
-    CK(cudaMemsetAsync(c->zero_region, 0, c->zero_bytes, s));
 
     FrameCtl* ctl = reinterpret_cast<FrameCtl*>(c->zero_region);
-    PreprocessLaunch p{};
+    FrameLaunch f{};
+    PreprocessLaunch& p = f.pre;
     p.scene = SceneArrays{ c->posop, c->cov_a, c->cov_b, c->sh, c->entity_count > 1 ? c->entity : nullptr, c->n, c->entity_count };
     p.models = c->models; p.cam = c->cam; p.vm = c->vm; p.pm = c->pm;
     p.ctl = ctl;
@@ -222,42 +273,65 @@ static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cud
     p.keys = c->keys[0]; p.vals = c->vals[0];
     p.capacity = c->capacity;
     p.width = c->width; p.height = c->height; p.sh_degree = std::min(sh_degree, 3u);  // GaussianEngine.cpp:366-370
-    CameraUbo cu;
-    memcpy(cu.f, ubo, sizeof(cu.f));  // by-value kernel argument: no per-frame H2D copy (updateCameraBuffer, :764-775)
-    CK(launch_setup(p, cu, s));
-    if (t) CK(cudaEventRecord(c->ev[1], s));
-    CK(launch_preprocess(p, s));
-    CK(launch_color(p, s));
-    if (c->keep_unsorted && c->capacity) {
-        if (c->unsorted_capacity < c->capacity) {
-            cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
-            c->unsorted_keys = nullptr; c->unsorted_vals = nullptr; c->unsorted_capacity = 0;
-            CK(cudaMalloc(&c->unsorted_keys, (size_t)c->capacity * 8));
-            CK(cudaMalloc(&c->unsorted_vals, (size_t)c->capacity * 4));
-            c->unsorted_capacity = c->capacity;
-        }
-        CK(cudaMemcpyAsync(c->unsorted_keys, c->keys[0], (size_t)c->capacity * 8, cudaMemcpyDeviceToDevice, s));
-        CK(cudaMemcpyAsync(c->unsorted_vals, c->vals[0], (size_t)c->capacity * 4, cudaMemcpyDeviceToDevice, s));
-    }
-    if (t) CK(cudaEventRecord(c->ev[2], s));
 
-    SortLaunch so{};
+    SortLaunch& so = f.sort;
     so.keys[0] = c->keys[0]; so.keys[1] = c->keys[1]; so.vals[0] = c->vals[0]; so.vals[1] = c->vals[1];
     so.ctl = ctl; so.plan = c->plan;
     so.lookback = reinterpret_cast<uint32_t*>(c->zero_region + c->off_lookback);
     so.capacity = c->capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
     so.packed_idx_bits = packed_idx_bits(c);
     so.packed_word_bits = c->packed_word_bits;
-    CK(launch_sort(so, UINT32_MAX, s, t ? c->ev[3] : nullptr));
-    if (t) CK(cudaEventRecord(c->ev[4], s));
 
-    RasterLaunch ra{};
+    RasterLaunch& ra = f.raster;
     ra.keys[0] = c->keys[0]; ra.keys[1] = c->keys[1]; ra.vals[0] = c->vals[0]; ra.vals[1] = c->vals[1];
     ra.plan = c->plan; ra.geo = c->geo; ra.color = c->color;
     ra.ranges = reinterpret_cast<uint32_t*>(c->zero_region + c->off_ranges);
     ra.out = out; ra.pitch = pitch; ra.capacity = c->capacity; ra.width = c->width; ra.height = c->height;
-    CK(launch_ranges(ra, s));
-    if (t) CK(cudaEventRecord(c->ev[5], s));
+
+    if (t) CK(cudaEventRecord(c->ev[0], s));
+    CameraUbo cu;
+    memcpy(cu.f, ubo, sizeof(cu.f));  // by-value kernel argument: no per-frame H2D copy (updateCameraBuffer, :764-775)
+    CK(launch_setup(p, cu, s));
+
+    bool replayed = false;
+    if (c->use_graph && !t) {
+        tpdcu_ctx::GraphSig sig;
+        memset(&sig, 0, sizeof(sig));
+        sig.zero_region = c->zero_region; sig.zero_bytes = c->zero_bytes; sig.keys0 = c->keys[0]; sig.keys1 = c->keys[1];
+        sig.geo = c->geo; sig.posop = c->posop; sig.n = c->n; sig.capacity = c->capacity; sig.width = c->width; sig.height = c->height;
+        sig.sh_degree = p.sh_degree; sig.packed_idx_bits = so.packed_idx_bits; sig.packed_word_bits = so.packed_word_bits;
+        sig.entity_count = c->entity_count; sig.keep_unsorted = c->keep_unsorted;
+        if (!(c->graph_valid && c->graph_sig == sig)) {
+            // (re)capture on a private stream: nothing executes during capture, and the legacy default stream cannot capture
+            drop_graph(c);
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeRelaxed);
+            int rc = TPDCU_OK;
+            if (e == cudaSuccess) {
+                rc = enqueue_middle(c, f, c->capture_stream, false);
+                e = cudaStreamEndCapture(c->capture_stream, &graph);
+            }
+            if (e == cudaSuccess && rc == TPDCU_OK && graph) e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e == cudaSuccess && rc == TPDCU_OK && c->graph_exec) {
+                c->graph_valid = true;
+                c->graph_sig = sig;
+                ++c->graph_captures;
+            } else {
+                cudaGetLastError();
+                drop_graph(c);
+                c->use_graph = false;  // capture is unavailable in this process: keep launching directly
+            }
+        }
+        if (c->graph_valid) {
+            CK(cudaGraphLaunch(c->graph_exec, s));
+            ++c->graph_launches;
+            replayed = true;
+        }
+    }
+    if (!replayed)
+        if (int r = enqueue_middle(c, f, s, t)) return r;
+
     CK(launch_blend(ra, s));
     if (t) CK(cudaEventRecord(c->ev[6], s));
 
@@ -359,9 +433,12 @@ int tpdcu_create(int device, tpdcu_ctx** out) {
     CKB(cudaMalloc(&c->plan, sizeof(SortPlan)));
     CKB(cudaMemset(c->plan, 0, sizeof(SortPlan)));
     CKB(cudaEventCreateWithFlags(&c->frame_done, cudaEventDisableTiming));
+    CKB(cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
     for (auto& e : c->ev) CKB(cudaEventCreate(&e));
     for (auto& e : c->sort_ev) CKB(cudaEventCreate(&e));
 #undef CKB
+    memset(&c->graph_sig, 0, sizeof(c->graph_sig));
+    if (cudaError_t e = init_sort_attributes()) return bail(fail(TPDCU_ERR_CUDA, std::string("init_sort_attributes: ") + cudaGetErrorString(e)));
     if (int r = ensure_status(c, 1)) return bail(r);
     *out = c;
     return TPDCU_OK;
@@ -375,6 +452,8 @@ void tpdcu_destroy(tpdcu_ctx* c) {
     free_pairs(c);
     cudaFree(c->cam); cudaFree(c->plan); cudaFree(c->zero_region); cudaFree(c->target);
     cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
+    drop_graph(c);
+    if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
     if (c->ext_mem) cudaDestroyExternalMemory(c->ext_mem);
     if (c->status) cudaFreeHost(c->status);
     if (c->frame_done) cudaEventDestroy(c->frame_done);
@@ -507,6 +586,8 @@ int tpdcu_bind_output_fd(tpdcu_ctx* c, int fd, size_t bytes) {
         cudaDestroyExternalMemory(mem);
         return fail(TPDCU_ERR_CUDA, std::string("cudaExternalMemoryGetMappedBuffer: ") + cudaGetErrorString(e));
     }
+    drop_graph(c);
+    if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
     if (c->ext_mem) cudaDestroyExternalMemory(c->ext_mem);
     c->ext_mem = mem;
     c->bound_out = reinterpret_cast<uint8_t*>(ptr);
@@ -714,6 +795,20 @@ int tpdcu_set_packed_word_bits(tpdcu_ctx* c, uint32_t bits) {
     if (int r = check_ready(c)) return r;
     if (bits < 1 || bits > 64) return fail(TPDCU_ERR_INVALID, "bits must be in [1, 64]");
     c->packed_word_bits = bits;
+    return TPDCU_OK;
+}
+
+int tpdcu_set_graph_replay(tpdcu_ctx* c, int enable, uint32_t* captures, uint32_t* launches) {
+    if (int r = check_ready(c)) return r;
+    if (enable >= 0) {
+        c->use_graph = enable != 0;
+        if (!c->use_graph) {
+            if (c->frame_pending) CK(cudaStreamSynchronize(c->last_stream));
+            drop_graph(c);
+        }
+    }
+    if (captures) *captures = c->graph_captures;
+    if (launches) *launches = c->graph_launches;
     return TPDCU_OK;
 }
 

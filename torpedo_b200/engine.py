@@ -300,6 +300,12 @@ class GaussianEngine:
     def set_packed_word_bits(self, bits: int) -> None:
         check(tpdcu().tpdcu_set_packed_word_bits(self._ctx, bits))
 
+    def graph_replay(self, enable: int = -1) -> tuple[int, int]:
+        """Switch CUDA-graph replay of the frame on (1) / off (0) or just query (-1); returns (captures, launches)."""
+        cap, lau = u32(0), u32(0)
+        check(tpdcu().tpdcu_set_graph_replay(self._ctx, enable, C.byref(cap), C.byref(lau)))
+        return cap.value, lau.value
+
     def capacity(self) -> int:
         c = u32(0)
         check(tpdcu().tpdcu_get_capacity(self._ctx, C.byref(c)))
