@@ -258,7 +258,7 @@ __device__ __forceinline__ Projected project_one(const PreprocessLaunch& a, uint
 }
 
 // One CTA = one partition of PRE_PART consecutive Gaussians (PRE_ITEMS per thread, striped so that loads coalesce).
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_kernel(PreprocessLaunch a) {
+__global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLaunch a) {
     __shared__ uint32_t s_part;
     __shared__ uint64_t s_base;                 // exclusive (visible, pairs) prefix of this partition
     __shared__ float s_vm[16], s_pm[16], s_v[12], s_focal[2];
