@@ -402,21 +402,66 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
     for (uint32_t k = 0; k < PRE_ITEMS; ++k)
         if (first + k * PRE_THREADS < n) a.out.offsets[first + k * PRE_THREADS] = base + local_excl[k];
 
-    // ---- duplication: the partition's pairs are emitted cooperatively, coalesced ---------------------
+    // ---- duplication (keygen.slang:47-53): the partition's pairs are emitted cooperatively ----------------------------
+    // Each thread takes groups of four CONSECUTIVE global slots (aligned to 4, so a full group is two 16-byte key stores
+    // and one 16-byte value store): one binary search finds the Gaussian owning the first slot, the next slots walk
+    // forward — the next tile of the same rectangle (x+1, wrapping to the next row) or the first tile of the next visible
+    // Gaussian. The reference loops serially per Gaussian; here big and small splats cost the same per pair.
     const uint32_t part_pairs = (uint32_t)total;
-    for (uint32_t j = tid; j < part_pairs; j += PRE_THREADS) {
+    const uint32_t slot_end = base + part_pairs;
+    const uint32_t id_base = part * PRE_PART;
+    for (uint32_t G0 = (base & ~3u) + 4u * tid; G0 < slot_end; G0 += 4u * PRE_THREADS) {
+        const uint32_t lo = max(G0, base), hi = min(G0 + 4u, slot_end);  // valid global slots of this group: [lo, hi)
+        const uint32_t j = lo - base;
         uint32_t g = 0;
 #pragma unroll
         for (uint32_t step = PRE_PART / 2; step >= 1; step >>= 1)
             if (s_off[g + step] <= j) g += step;
+        uint32_t w = s_w[g], xy = s_xy[g], depth = s_depth[g];
         const uint32_t r = j - s_off[g];
-        const uint32_t w = s_w[g], xy = s_xy[g];
-        const uint32_t ry = r / w, rx = r - ry * w;
-        const uint32_t tile = ((xy >> 16) + ry) * gx + ((xy & 0xffffu) + rx);
-        const uint32_t out = base + j;
-        if (out < a.capacity) {
-            a.keys[out] = ((uint64_t)tile << 32) | s_depth[g];
-            a.vals[out] = part * PRE_PART + g;
+        const uint32_t ry = r / w;
+        uint32_t rx = r - ry * w;
+        uint32_t row = ((xy >> 16) + ry) * gx + (xy & 0xffffu);  // tile id of the rectangle's column 0 in the current row
+        uint32_t next_off = g + 1 < PRE_PART ? s_off[g + 1] : 0xffffffffu;
+        uint64_t key[4];
+        uint32_t val[4];
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            const uint32_t G = G0 + q;
+            if (G >= lo && G < hi) {
+                if (G > lo) {
+                    const uint32_t jq = G - base;
+                    if (jq >= next_off) {  // first tile of the next visible Gaussian (zero-count ones share their offset)
+                        do {
+                            ++g;
+                            next_off = g + 1 < PRE_PART ? s_off[g + 1] : 0xffffffffu;
+                        } while (jq >= next_off);
+                        w = s_w[g]; xy = s_xy[g]; depth = s_depth[g];
+                        rx = 0;
+                        row = (xy >> 16) * gx + (xy & 0xffffu);
+                    } else if (++rx == w) {
+                        rx = 0;
+                        row += gx;
+                    }
+                }
+                key[q] = ((uint64_t)(row + rx) << 32) | depth;
+                val[q] = id_base + g;
+            }
+        }
+        if (lo == G0 && hi == G0 + 4u && G0 + 4u <= a.capacity) {
+            ulonglong2* kp = reinterpret_cast<ulonglong2*>(a.keys + G0);
+            kp[0] = make_ulonglong2(key[0], key[1]);
+            kp[1] = make_ulonglong2(key[2], key[3]);
+            *reinterpret_cast<uint4*>(a.vals + G0) = make_uint4(val[0], val[1], val[2], val[3]);
+        } else {
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                const uint32_t G = G0 + q;
+                if (G >= lo && G < hi && G < a.capacity) {
+                    a.keys[G] = key[q];
+                    a.vals[G] = val[q];
+                }
+            }
         }
     }
 }
