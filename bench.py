@@ -327,8 +327,10 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "n_gaussians": n, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
                        "views": f"ring of {RING_VIEWS} cameras through the garden eye, view = step*N + rank",
                        "parallelism": f"views sharded over {world} GPU(s), scene replicated (NCCL broadcast + frame gather)",
+                       "pipelining": "2 frames in flight (as the reference, SurfaceRenderer.h:66): front of frame k+1 overlaps the blend of frame k",
                        "l2_policy": "inputs larger than L2 (scene arrays 1.4 GB, pair buffers 0.4 GB vs 126 MB L2); a different view every step"},
             "pairs": int(stage_pairs), "visible": int(visible), "capacity_ok": bool(cap_ok),
+            "frames_in_flight": 2, "single_frame_latency_ms": stages["frame"],
             "stages_ms": stages,
             "sort_gkeys_per_s": stage_pairs / (sort_ms * 1e-3) / 1e9 if sort_ms > 0 else None,
             "sort": dict(sort_info, passes_run=passes, bytes_per_pair=(8 + 20 + 16 * (passes - 1)) if sort_info["packed"] else (8 + 24 * passes)),

@@ -132,6 +132,12 @@ int tpdcu_set_packed_word_bits(tpdcu_ctx* ctx, uint32_t bits);
  * into a CUDA graph and replayed (the reference re-records two command buffers every frame, GaussianEngine.cpp:637-697).
  * enable: 1/0 to switch replay on/off, -1 to only query. captures/launches (nullable): counters since tpdcu_create. */
 int tpdcu_set_graph_replay(tpdcu_ctx* ctx, int enable, uint32_t* captures, uint32_t* launches);
+/* Frames in flight (1 or 2, default 2), the counterpart of the reference's per-frame Frame objects (GaussianEngine.h:104-117,
+ * SurfaceRenderer.h:66): with 2, consecutive tpdcu_raster calls alternate between two sets of per-frame buffers on private
+ * streams so that the memory-bound front of frame k+1 overlaps the SM-bound blend of frame k. Ordering seen by the caller
+ * is unchanged: the blend waits for `stream`, `stream` waits for the frame. tpdcu_finish/read_* refer to the newest frame;
+ * an older frame that overflowed is re-rendered only if it went to a different target. */
+int tpdcu_set_frames_in_flight(tpdcu_ctx* ctx, int frames);
 /* Current pair-buffer capacity (grow-only, like GaussianEngine::reallocateBuffers :793-804) */
 int tpdcu_get_capacity(tpdcu_ctx* ctx, uint32_t* capacity_pairs);
 int tpdcu_reserve_pairs(tpdcu_ctx* ctx, uint32_t capacity_pairs);

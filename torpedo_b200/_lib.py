@@ -44,6 +44,7 @@ TPDCU_SYMBOLS = {
     "tpdcu_get_sort_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
     "tpdcu_set_packed_word_bits": (i32, [vp, u32]),
     "tpdcu_set_graph_replay": (i32, [vp, i32, C.POINTER(u32), C.POINTER(u32)]),
+    "tpdcu_set_frames_in_flight": (i32, [vp, i32]),
     "tpdcu_get_capacity": (i32, [vp, C.POINTER(u32)]),
     "tpdcu_reserve_pairs": (i32, [vp, u32]),
     "tpdcu_sort_pairs_device": (i32, [vp, vp, vp, u32, u32, vp]),

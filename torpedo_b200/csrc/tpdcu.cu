@@ -5,8 +5,12 @@
 // draw() -> read_frame / external-memory output. What differs by design:
 //   * no mid-frame GPU->CPU read-back of tilesRendered (GaussianEngine.cpp:662-674): P stays on the device,
 //     launches are sized by the grow-only pair capacity and an overflowing frame is re-rendered lazily;
-//   * 1 fused preprocess launch + (2 + <=6) sort launches + 2 raster launches per frame instead of
-//     2 + 1 + 92 + 2 dispatches with 95 pipeline barriers (GaussianEngine.cpp:777-863).
+//   * 13 launches per frame (replayed from a CUDA graph) instead of 2 + 1 + 92 + 2 dispatches with 95 pipeline
+//     barriers (GaussianEngine.cpp:777-863);
+//   * two frames in flight, like the reference's Frame objects (GaussianEngine.h:104-117, SurfaceRenderer.h:66): every
+//     frame slot owns its splat arrays, pair buffers and a private stream, so the memory-bound front of frame k+1
+//     (preprocess, sort) overlaps the SM-bound blend of frame k. Only the blend is ordered after the caller's stream
+//     (it is what writes the target); the caller's stream then waits for the frame.
 #include "../../include/tpdcu.h"
 #include "common.cuh"
 
@@ -44,44 +48,84 @@ struct FrameStatus {  // pinned host mirror of what a frame reports back
 };
 static_assert(offsetof(SortPlan, packed_overflow) == 9 * sizeof(uint32_t), "FrameStatus mirrors the head of SortPlan");
 
+constexpr int MAX_SLOTS = 2;
+
+struct GraphSig {  // everything a captured frame bakes in
+    const void* zero_region; size_t zero_bytes; const void* keys0; const void* keys1; const void* geo; const void* posop;
+    uint32_t n, capacity, width, height, sh_degree, packed_idx_bits, packed_word_bits, entity_count;
+    uint32_t keep_unsorted;
+    bool operator==(const GraphSig& o) const { return memcmp(this, &o, sizeof(GraphSig)) == 0; }
+};
+
+// One frame in flight: the per-frame twin of GaussianEngine::Frame (GaussianEngine.h:104-117).
+struct FrameSlot {
+    // per-Gaussian outputs of the preprocess stage
+    SplatGeo* geo = nullptr;
+    float4* color = nullptr;
+    float2* depth_radius = nullptr;
+    uint32_t* offsets = nullptr;
+    uint32_t n_alloc = 0;
+    // camera-derived constants and model matrices
+    FrameCam* cam = nullptr;
+    float* models = nullptr;
+    float* vm = nullptr;
+    float* pm = nullptr;
+    uint32_t entity_alloc = 0;
+    uint64_t models_version = 0;
+    // sort / raster state
+    SortPlan* plan = nullptr;
+    uint8_t* zero_region = nullptr;
+    size_t zero_bytes = 0, off_scan_desc = 0, off_ranges = 0, off_lookback = 0;
+    uint32_t zero_n = 0, zero_capacity = 0, zero_tiles = 0;
+    uint32_t capacity = 0;
+    uint64_t* keys[2] = { nullptr, nullptr };
+    uint32_t* vals[2] = { nullptr, nullptr };
+    uint64_t* unsorted_keys = nullptr;
+    uint32_t* unsorted_vals = nullptr;
+    uint32_t unsorted_capacity = 0;
+    // execution
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, done = nullptr;
+    bool graph_valid = false;
+    GraphSig graph_sig;
+    cudaGraphExec_t graph_exec = nullptr;
+    // the frame it holds
+    bool pending = false;
+    float ubo[TPDCU_CAMERA_FLOATS];
+    uint32_t sh_degree = 3;
+    uint8_t* out = nullptr;
+    size_t pitch = 0;
+    cudaStream_t user_stream = nullptr;
+    uint32_t status_index = 0;
+};
+
 struct tpdcu_ctx {
     int device = 0;
     int sm_count = 0;
     std::string device_name;
 
-    // scene
+    // scene (shared by the frame slots, read-only while rendering)
     uint32_t n = 0, entity_count = 0;
     float4* posop = nullptr;
     float4* cov_a = nullptr;
     float2* cov_b = nullptr;
     float4* sh = nullptr;
     uint32_t* entity = nullptr;
-    SplatGeo* geo = nullptr;
-    float4* color = nullptr;
-    float2* depth_radius = nullptr;
-    uint32_t* offsets = nullptr;
-    float* models = nullptr;
-    float* vm = nullptr;
-    float* pm = nullptr;
     std::vector<float> models_host;
-    bool models_dirty = false;
+    uint64_t models_version = 1;
 
-    // per-frame state
-    FrameCam* cam = nullptr;
-    SortPlan* plan = nullptr;
-    uint8_t* zero_region = nullptr;
-    size_t zero_bytes = 0;
-    size_t off_scan_desc = 0, off_ranges = 0, off_lookback = 0;
-    uint32_t zero_n = 0, zero_capacity = 0, zero_tiles = 0;
-    uint32_t capacity = 0;
-    uint64_t* keys[2] = { nullptr, nullptr };
-    uint32_t* vals[2] = { nullptr, nullptr };
+    FrameSlot slots[MAX_SLOTS];
+    int frames_in_flight = 2;
+    int next_slot = 0;
+    int last_slot = -1;  // slot of the most recent frame (what finish / read_* / introspection refer to)
+    bool frame_valid = false;
+
     uint32_t packed_word_bits = 64;
     bool packed_disabled = false;  // a frame whose depth range did not fit packed sort words switches the context to pair mode
     bool keep_unsorted = false;
-    uint64_t* unsorted_keys = nullptr;
-    uint32_t* unsorted_vals = nullptr;
-    uint32_t unsorted_capacity = 0;
+    bool use_graph = true;
+    uint32_t graph_launches = 0, graph_captures = 0;
+    cudaStream_t capture_stream = nullptr;
 
     // target
     uint32_t width = 0, height = 0;
@@ -91,37 +135,18 @@ struct tpdcu_ctx {
     size_t bound_pitch = 0;
     cudaExternalMemory_t ext_mem = nullptr;
 
-    // last frame
-    bool frame_pending = false, frame_valid = false;
-    float last_ubo[TPDCU_CAMERA_FLOATS];
-    uint32_t last_sh_degree = 3;
-    cudaStream_t last_stream = nullptr;
-    FrameStatus* status = nullptr;  // pinned, status_slots entries
+    FrameStatus* status = nullptr;  // pinned, status_slots entries; entries [0, MAX_SLOTS) belong to the frame slots
     uint32_t status_slots = 0;
-    cudaEvent_t frame_done = nullptr;
+    std::vector<uint32_t> ran_capacity;  // per status entry: the pair capacity the frame was enqueued with
 
     bool timing = false;
     cudaEvent_t ev[7] = {};
     float stage_ms[TPDCU_NUM_STAGES] = {};
 
-    // CUDA graph of the frame's parameter-invariant middle section (memset .. ranges); re-captured when anything it bakes in changes
-    struct GraphSig {
-        const void* zero_region; size_t zero_bytes; const void* keys0; const void* keys1; const void* geo; const void* posop;
-        uint32_t n, capacity, width, height, sh_degree, packed_idx_bits, packed_word_bits, entity_count;
-        bool keep_unsorted;
-        bool operator==(const GraphSig& o) const { return memcmp(this, &o, sizeof(GraphSig)) == 0; }
-    };
-    bool use_graph = true;
-    bool graph_valid = false;
-    GraphSig graph_sig{};
-    cudaGraphExec_t graph_exec = nullptr;
-    cudaStream_t capture_stream = nullptr;
-    uint32_t graph_launches = 0, graph_captures = 0;
-
     // standalone sort
     cudaEvent_t sort_ev[2] = {};
-    float sort_ms = 0.f;
-    uint32_t sort_passes = 0;
+    cudaStream_t sort_stream = nullptr;
+    bool sort_done = false;
 };
 
 static uint32_t bit_length(uint32_t v) {
@@ -146,59 +171,95 @@ static uint32_t packed_idx_bits(const tpdcu_ctx* c) {
     return (idx_bits + tile_bits <= 40u) ? idx_bits : 0u;
 }
 
+static void drop_graph(FrameSlot& f) {
+    if (f.graph_exec) cudaGraphExecDestroy(f.graph_exec);
+    f.graph_exec = nullptr;
+    f.graph_valid = false;
+}
+
+static void free_slot_scene(FrameSlot& f) {
+    cudaFree(f.geo); cudaFree(f.color); cudaFree(f.depth_radius); cudaFree(f.offsets);
+    cudaFree(f.models); cudaFree(f.vm); cudaFree(f.pm);
+    f.geo = nullptr; f.color = nullptr; f.depth_radius = nullptr; f.offsets = nullptr;
+    f.models = f.vm = f.pm = nullptr;
+    f.n_alloc = 0; f.entity_alloc = 0; f.models_version = 0;
+    drop_graph(f);
+}
+
+static void free_slot_pairs(FrameSlot& f) {
+    for (int i = 0; i < 2; ++i) { cudaFree(f.keys[i]); cudaFree(f.vals[i]); f.keys[i] = nullptr; f.vals[i] = nullptr; }
+    f.capacity = 0;
+    drop_graph(f);
+}
+
 static void free_scene(tpdcu_ctx* c) {
     cudaFree(c->posop); cudaFree(c->cov_a); cudaFree(c->cov_b); cudaFree(c->sh); cudaFree(c->entity);
-    cudaFree(c->geo); cudaFree(c->color); cudaFree(c->depth_radius); cudaFree(c->offsets); cudaFree(c->models); cudaFree(c->vm); cudaFree(c->pm);
-    c->posop = c->cov_a = nullptr; c->cov_b = nullptr; c->sh = nullptr; c->entity = nullptr; c->geo = nullptr; c->color = nullptr; c->depth_radius = nullptr;
-    c->offsets = nullptr; c->models = c->vm = c->pm = nullptr;
+    c->posop = c->cov_a = nullptr; c->cov_b = nullptr; c->sh = nullptr; c->entity = nullptr;
     c->n = 0; c->entity_count = 0;
+    for (auto& f : c->slots) free_slot_scene(f);
 }
 
-static void free_pairs(tpdcu_ctx* c) {
-    for (int i = 0; i < 2; ++i) { cudaFree(c->keys[i]); cudaFree(c->vals[i]); c->keys[i] = nullptr; c->vals[i] = nullptr; }
-    c->capacity = 0;
+static int ensure_slot_scene(tpdcu_ctx* c, FrameSlot& f) {
+    if (f.n_alloc != c->n || f.entity_alloc != c->entity_count) {
+        free_slot_scene(f);
+        CK(cudaMalloc(&f.geo, (size_t)c->n * sizeof(SplatGeo)));
+        CK(cudaMalloc(&f.color, (size_t)c->n * sizeof(float4)));
+        CK(cudaMalloc(&f.depth_radius, (size_t)c->n * sizeof(float2)));
+        CK(cudaMalloc(&f.offsets, ((size_t)c->n + 1) * sizeof(uint32_t)));
+        CK(cudaMalloc(&f.models, (size_t)c->entity_count * 16 * sizeof(float)));
+        CK(cudaMalloc(&f.vm, (size_t)c->entity_count * 16 * sizeof(float)));
+        CK(cudaMalloc(&f.pm, (size_t)c->entity_count * 16 * sizeof(float)));
+        f.n_alloc = c->n;
+        f.entity_alloc = c->entity_count;
+    }
+    return TPDCU_OK;
 }
 
-static int ensure_pairs(tpdcu_ctx* c, uint32_t want) {
-    if (want <= c->capacity) return TPDCU_OK;
+static int ensure_pairs(FrameSlot& f, uint32_t want) {
+    if (want <= f.capacity) return TPDCU_OK;
     // grow-only (GaussianEngine.cpp:671-674,793-804), rounded to whole sort tiles
-    uint64_t cap64 = align_up(want, SORT_TILE);
+    const uint64_t cap64 = align_up(want, SORT_TILE);
     if (cap64 > 0xffffffffull - SORT_TILE) return fail(TPDCU_ERR_INVALID, "pair capacity exceeds 2^32");
-    free_pairs(c);
+    free_slot_pairs(f);
     const uint32_t cap = (uint32_t)cap64;
     for (int i = 0; i < 2; ++i) {
-        CK(cudaMalloc(&c->keys[i], (size_t)cap * sizeof(uint64_t)));
-        CK(cudaMalloc(&c->vals[i], (size_t)cap * sizeof(uint32_t)));
+        CK(cudaMalloc(&f.keys[i], (size_t)cap * sizeof(uint64_t)));
+        CK(cudaMalloc(&f.vals[i], (size_t)cap * sizeof(uint32_t)));
     }
-    c->capacity = cap;
+    f.capacity = cap;
     return TPDCU_OK;
 }
 
 // The per-frame zeroed region: FrameCtl | scan descriptors | tile ranges | onesweep look-back arrays
-static int ensure_zero_region(tpdcu_ctx* c, uint32_t passes) {
+static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f) {
     const uint32_t tiles = tiles_of(c);
-    if (c->zero_region && c->zero_n == c->n && c->zero_capacity == c->capacity && c->zero_tiles == tiles) return TPDCU_OK;
-    cudaFree(c->zero_region);
-    c->zero_region = nullptr;
+    if (f.zero_region && f.zero_n == c->n && f.zero_capacity == f.capacity && f.zero_tiles == tiles) return TPDCU_OK;
+    cudaFree(f.zero_region);
+    f.zero_region = nullptr;
+    drop_graph(f);
     const uint32_t pre_parts = (c->n + PRE_PART - 1) / PRE_PART;
     size_t off = align_up(sizeof(FrameCtl), 256);
-    c->off_scan_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
-    c->off_ranges = off;    off = align_up(off + (size_t)tiles * 2 * sizeof(uint32_t), 256);
-    c->off_lookback = off;  off = align_up(off + (size_t)SORT_MAX_PASSES * sort_parts(c->capacity) * SORT_BINS * sizeof(uint32_t), 256);
-    (void)passes;
-    CK(cudaMalloc(&c->zero_region, off));
-    c->zero_bytes = off;
-    c->zero_n = c->n; c->zero_capacity = c->capacity; c->zero_tiles = tiles;
+    f.off_scan_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
+    f.off_ranges = off;    off = align_up(off + (size_t)tiles * 2 * sizeof(uint32_t), 256);
+    f.off_lookback = off;  off = align_up(off + (size_t)SORT_MAX_PASSES * sort_parts(f.capacity) * SORT_BINS * sizeof(uint32_t), 256);
+    CK(cudaMalloc(&f.zero_region, off));
+    f.zero_bytes = off;
+    f.zero_n = c->n; f.zero_capacity = f.capacity; f.zero_tiles = tiles;
     return TPDCU_OK;
 }
 
 static int ensure_status(tpdcu_ctx* c, uint32_t slots) {
     if (slots <= c->status_slots) return TPDCU_OK;
-    if (c->status) cudaFreeHost(c->status);
-    c->status = nullptr;
-    CK(cudaMallocHost(&c->status, sizeof(FrameStatus) * slots));
-    memset(c->status, 0, sizeof(FrameStatus) * slots);
+    FrameStatus* fresh = nullptr;
+    CK(cudaMallocHost(&fresh, sizeof(FrameStatus) * slots));
+    memset(fresh, 0, sizeof(FrameStatus) * slots);
+    if (c->status) {
+        memcpy(fresh, c->status, sizeof(FrameStatus) * c->status_slots);
+        cudaFreeHost(c->status);
+    }
+    c->status = fresh;
     c->status_slots = slots;
+    c->ran_capacity.resize(slots, 0u);
     return TPDCU_OK;
 }
 
@@ -212,6 +273,12 @@ static int ensure_target(tpdcu_ctx* c) {
     return TPDCU_OK;
 }
 
+static int sync_slots(tpdcu_ctx* c) {
+    for (auto& f : c->slots)
+        if (f.stream) CK(cudaStreamSynchronize(f.stream));
+    return TPDCU_OK;
+}
+
 struct FrameLaunch {
     PreprocessLaunch pre;
     SortLaunch sort;
@@ -219,144 +286,160 @@ struct FrameLaunch {
 };
 
 // The part of a frame whose launch parameters do not change from frame to frame: everything between the camera setup and
-// the blend. Either enqueued directly or captured once into a CUDA graph and replayed (13 launches -> 1 graph launch).
-static int enqueue_middle(tpdcu_ctx* c, const FrameLaunch& f, cudaStream_t s, bool timing) {
-    CK(cudaMemsetAsync(c->zero_region, 0, c->zero_bytes, s));
+// the blend. Either enqueued directly or captured once into a CUDA graph and replayed.
+static int enqueue_middle(tpdcu_ctx* c, FrameSlot& f, const FrameLaunch& l, cudaStream_t s, bool timing) {
+    CK(cudaMemsetAsync(f.zero_region, 0, f.zero_bytes, s));
     if (timing) CK(cudaEventRecord(c->ev[1], s));
-    CK(launch_preprocess(f.pre, s));
-    CK(launch_color(f.pre, s));
-    if (c->keep_unsorted && c->capacity) {
-        CK(cudaMemcpyAsync(c->unsorted_keys, c->keys[0], (size_t)c->capacity * 8, cudaMemcpyDeviceToDevice, s));
-        CK(cudaMemcpyAsync(c->unsorted_vals, c->vals[0], (size_t)c->capacity * 4, cudaMemcpyDeviceToDevice, s));
+    CK(launch_preprocess(l.pre, s));
+    CK(launch_color(l.pre, s));
+    if (c->keep_unsorted && f.capacity) {
+        CK(cudaMemcpyAsync(f.unsorted_keys, f.keys[0], (size_t)f.capacity * 8, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(f.unsorted_vals, f.vals[0], (size_t)f.capacity * 4, cudaMemcpyDeviceToDevice, s));
     }
     if (timing) CK(cudaEventRecord(c->ev[2], s));
-    CK(launch_sort(f.sort, UINT32_MAX, s, timing ? c->ev[3] : nullptr));
+    CK(launch_sort(l.sort, UINT32_MAX, s, timing ? c->ev[3] : nullptr));
     if (timing) CK(cudaEventRecord(c->ev[4], s));
-    CK(launch_ranges(f.raster, s));
+    CK(launch_ranges(l.raster, s));
     if (timing) CK(cudaEventRecord(c->ev[5], s));
     return TPDCU_OK;
 }
 
-static void drop_graph(tpdcu_ctx* c) {
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-    c->graph_exec = nullptr;
-    c->graph_valid = false;
-}
-
-// Enqueue one frame. No host synchronisation.
-static int enqueue_frame(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cudaStream_t s, uint8_t* out, size_t pitch,
-                         uint32_t slot) {
-    const uint32_t end_bit = frame_end_bit(c);
-    const uint32_t passes = (end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
-    if (int r = ensure_zero_region(c, passes)) return r;
-    if (c->models_dirty) {
-        CK(cudaMemcpyAsync(c->models, c->models_host.data(), sizeof(float) * 16 * c->entity_count, cudaMemcpyHostToDevice, s));
-        c->models_dirty = false;
-    }
-    if (c->keep_unsorted && c->capacity && c->unsorted_capacity < c->capacity) {
-        cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
-        c->unsorted_keys = nullptr; c->unsorted_vals = nullptr; c->unsorted_capacity = 0;
-        CK(cudaMalloc(&c->unsorted_keys, (size_t)c->capacity * 8));
-        CK(cudaMalloc(&c->unsorted_vals, (size_t)c->capacity * 4));
-        c->unsorted_capacity = c->capacity;
-    }
+// Enqueue the frame described by the slot (f.ubo, f.sh_degree, f.out, f.pitch, f.user_stream, f.status_index).
+// No host synchronisation. With stage timing everything runs on the caller's stream; otherwise the front of the frame runs
+// on the slot's stream unordered with the caller's stream, the blend waits for the caller's stream (it writes the target)
+// and the caller's stream waits for the frame.
+static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f) {
+    if (int r = ensure_slot_scene(c, f)) return r;
+    if (f.capacity == 0)
+        if (int r = ensure_pairs(f, SORT_TILE)) return r;
+    if (int r = ensure_zero_region(c, f)) return r;
     const bool t = c->timing;
+    cudaStream_t user = f.user_stream;
+    cudaStream_t s = t ? user : f.stream;
 
-    FrameCtl* ctl = reinterpret_cast<FrameCtl*>(c->zero_region);
-    FrameLaunch f{};
-    PreprocessLaunch& p = f.pre;
+    if (f.models_version != c->models_version) {
+        CK(cudaMemcpyAsync(f.models, c->models_host.data(), sizeof(float) * 16 * c->entity_count, cudaMemcpyHostToDevice, s));
+        f.models_version = c->models_version;
+    }
+    if (c->keep_unsorted && f.unsorted_capacity < f.capacity) {
+        cudaFree(f.unsorted_keys); cudaFree(f.unsorted_vals);
+        f.unsorted_keys = nullptr; f.unsorted_vals = nullptr; f.unsorted_capacity = 0;
+        drop_graph(f);
+        CK(cudaMalloc(&f.unsorted_keys, (size_t)f.capacity * 8));
+        CK(cudaMalloc(&f.unsorted_vals, (size_t)f.capacity * 4));
+        f.unsorted_capacity = f.capacity;
+    }
+
+    const uint32_t end_bit = frame_end_bit(c);
+    FrameCtl* ctl = reinterpret_cast<FrameCtl*>(f.zero_region);
+    FrameLaunch l{};
+    PreprocessLaunch& p = l.pre;
     p.scene = SceneArrays{ c->posop, c->cov_a, c->cov_b, c->sh, c->entity_count > 1 ? c->entity : nullptr, c->n, c->entity_count };
-    p.models = c->models; p.cam = c->cam; p.vm = c->vm; p.pm = c->pm;
+    p.models = f.models; p.cam = f.cam; p.vm = f.vm; p.pm = f.pm;
     p.ctl = ctl;
-    p.scan_desc = reinterpret_cast<uint64_t*>(c->zero_region + c->off_scan_desc);
-    p.out = SplatArrays{ c->geo, c->color, c->depth_radius, c->offsets };
-    p.keys = c->keys[0]; p.vals = c->vals[0];
-    p.capacity = c->capacity;
-    p.width = c->width; p.height = c->height; p.sh_degree = std::min(sh_degree, 3u);  // GaussianEngine.cpp:366-370
+    p.scan_desc = reinterpret_cast<uint64_t*>(f.zero_region + f.off_scan_desc);
+    p.out = SplatArrays{ f.geo, f.color, f.depth_radius, f.offsets };
+    p.keys = f.keys[0]; p.vals = f.vals[0];
+    p.capacity = f.capacity;
+    p.width = c->width; p.height = c->height; p.sh_degree = std::min(f.sh_degree, 3u);  // GaussianEngine.cpp:366-370
 
-    SortLaunch& so = f.sort;
-    so.keys[0] = c->keys[0]; so.keys[1] = c->keys[1]; so.vals[0] = c->vals[0]; so.vals[1] = c->vals[1];
-    so.ctl = ctl; so.plan = c->plan;
-    so.lookback = reinterpret_cast<uint32_t*>(c->zero_region + c->off_lookback);
-    so.capacity = c->capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
+    SortLaunch& so = l.sort;
+    so.keys[0] = f.keys[0]; so.keys[1] = f.keys[1]; so.vals[0] = f.vals[0]; so.vals[1] = f.vals[1];
+    so.ctl = ctl; so.plan = f.plan;
+    so.lookback = reinterpret_cast<uint32_t*>(f.zero_region + f.off_lookback);
+    so.capacity = f.capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
     so.packed_idx_bits = packed_idx_bits(c);
     so.packed_word_bits = c->packed_word_bits;
 
-    RasterLaunch& ra = f.raster;
-    ra.keys[0] = c->keys[0]; ra.keys[1] = c->keys[1]; ra.vals[0] = c->vals[0]; ra.vals[1] = c->vals[1];
-    ra.plan = c->plan; ra.geo = c->geo; ra.color = c->color;
-    ra.ranges = reinterpret_cast<uint32_t*>(c->zero_region + c->off_ranges);
-    ra.out = out; ra.pitch = pitch; ra.capacity = c->capacity; ra.width = c->width; ra.height = c->height;
+    RasterLaunch& ra = l.raster;
+    ra.keys[0] = f.keys[0]; ra.keys[1] = f.keys[1]; ra.vals[0] = f.vals[0]; ra.vals[1] = f.vals[1];
+    ra.plan = f.plan; ra.geo = f.geo; ra.color = f.color;
+    ra.ranges = reinterpret_cast<uint32_t*>(f.zero_region + f.off_ranges);
+    ra.out = f.out; ra.pitch = f.pitch; ra.capacity = f.capacity; ra.width = c->width; ra.height = c->height;
 
     if (t) CK(cudaEventRecord(c->ev[0], s));
     CameraUbo cu;
-    memcpy(cu.f, ubo, sizeof(cu.f));  // by-value kernel argument: no per-frame H2D copy (updateCameraBuffer, :764-775)
+    memcpy(cu.f, f.ubo, sizeof(cu.f));  // by-value kernel argument: no per-frame H2D copy (updateCameraBuffer, :764-775)
     CK(launch_setup(p, cu, s));
 
     bool replayed = false;
     if (c->use_graph && !t) {
-        tpdcu_ctx::GraphSig sig;
+        GraphSig sig;
         memset(&sig, 0, sizeof(sig));
-        sig.zero_region = c->zero_region; sig.zero_bytes = c->zero_bytes; sig.keys0 = c->keys[0]; sig.keys1 = c->keys[1];
-        sig.geo = c->geo; sig.posop = c->posop; sig.n = c->n; sig.capacity = c->capacity; sig.width = c->width; sig.height = c->height;
+        sig.zero_region = f.zero_region; sig.zero_bytes = f.zero_bytes; sig.keys0 = f.keys[0]; sig.keys1 = f.keys[1];
+        sig.geo = f.geo; sig.posop = c->posop; sig.n = c->n; sig.capacity = f.capacity; sig.width = c->width; sig.height = c->height;
         sig.sh_degree = p.sh_degree; sig.packed_idx_bits = so.packed_idx_bits; sig.packed_word_bits = so.packed_word_bits;
-        sig.entity_count = c->entity_count; sig.keep_unsorted = c->keep_unsorted;
-        if (!(c->graph_valid && c->graph_sig == sig)) {
-            // (re)capture on a private stream: nothing executes during capture, and the legacy default stream cannot capture
-            drop_graph(c);
+        sig.entity_count = c->entity_count; sig.keep_unsorted = c->keep_unsorted ? 1u : 0u;
+        if (!(f.graph_valid && f.graph_sig == sig)) {
+            // (re)capture on a private stream: nothing executes during capture
+            drop_graph(f);
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamBeginCapture(c->capture_stream, cudaStreamCaptureModeRelaxed);
             int rc = TPDCU_OK;
             if (e == cudaSuccess) {
-                rc = enqueue_middle(c, f, c->capture_stream, false);
+                rc = enqueue_middle(c, f, l, c->capture_stream, false);
                 e = cudaStreamEndCapture(c->capture_stream, &graph);
             }
-            if (e == cudaSuccess && rc == TPDCU_OK && graph) e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+            if (e == cudaSuccess && rc == TPDCU_OK && graph) e = cudaGraphInstantiate(&f.graph_exec, graph, 0);
             if (graph) cudaGraphDestroy(graph);
-            if (e == cudaSuccess && rc == TPDCU_OK && c->graph_exec) {
-                c->graph_valid = true;
-                c->graph_sig = sig;
+            if (e == cudaSuccess && rc == TPDCU_OK && f.graph_exec) {
+                f.graph_valid = true;
+                f.graph_sig = sig;
                 ++c->graph_captures;
             } else {
                 cudaGetLastError();
-                drop_graph(c);
+                drop_graph(f);
                 c->use_graph = false;  // capture is unavailable in this process: keep launching directly
             }
         }
-        if (c->graph_valid) {
-            CK(cudaGraphLaunch(c->graph_exec, s));
+        if (f.graph_valid) {
+            CK(cudaGraphLaunch(f.graph_exec, s));
             ++c->graph_launches;
             replayed = true;
         }
     }
     if (!replayed)
-        if (int r = enqueue_middle(c, f, s, t)) return r;
+        if (int r = enqueue_middle(c, f, l, s, t)) return r;
 
+    if (!t) {  // the blend writes the caller's target: order it after whatever the caller's stream did with that memory
+        CK(cudaEventRecord(f.fork, user));
+        CK(cudaStreamWaitEvent(s, f.fork, 0));
+    }
     CK(launch_blend(ra, s));
     if (t) CK(cudaEventRecord(c->ev[6], s));
 
-    CK(cudaMemcpyAsync(&c->status[slot].pairs_total, &ctl->pairs_total, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&c->status[slot].n, c->plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    return TPDCU_OK;
-}
-
-// Does a finished frame have to be rendered again (buffers too small / packed words too narrow)? Adjusts the context.
-static int frame_needs_rerender(tpdcu_ctx* c, const FrameStatus& st, bool* again) {
-    *again = false;
-    if (st.pairs_total > c->capacity) {
-        *again = true;
-        return TPDCU_OK;
-    }
-    if (st.packed_overflow) {
-        c->packed_disabled = true;
-        *again = true;
-    }
+    FrameStatus* st = &c->status[f.status_index];
+    CK(cudaMemcpyAsync(&st->pairs_total, &ctl->pairs_total, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&st->n, f.plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(f.done, s));
+    if (!t) CK(cudaStreamWaitEvent(user, f.done, 0));
+    c->ran_capacity[f.status_index] = f.capacity;
+    f.pending = true;
     return TPDCU_OK;
 }
 
 static uint32_t grown_capacity(uint32_t pairs) {
     const uint64_t want = (uint64_t)pairs + pairs / 8 + SORT_TILE;  // 12.5 % head-room against view changes
     return (uint32_t)std::min<uint64_t>(want, 0xffffffffull - 2 * SORT_TILE);
+}
+
+// Wait for the slot's frame; if it overflowed the pair buffers or the packed word, fix the cause and render it again.
+static int settle_slot(tpdcu_ctx* c, FrameSlot& f) {
+    for (int attempt = 0; f.pending; ++attempt) {
+        CK(cudaEventSynchronize(f.done));
+        const FrameStatus& st = c->status[f.status_index];
+        const bool grow = st.pairs_total > f.capacity;
+        const bool unpack = !grow && st.packed_overflow;
+        if (!grow && !unpack) { f.pending = false; break; }
+        if (attempt >= 5) return fail(TPDCU_ERR_STATE, "frame kept overflowing its buffers");
+        if (unpack) c->packed_disabled = true;
+        CK(cudaStreamSynchronize(f.stream));
+        CK(cudaStreamSynchronize(f.user_stream));
+        if (grow)
+            if (int r = ensure_pairs(f, grown_capacity(st.pairs_total))) return r;
+        if (int r = enqueue_frame(c, f)) return r;
+    }
+    return TPDCU_OK;
 }
 
 static uint8_t* out_ptr(tpdcu_ctx* c, size_t* pitch) {
@@ -372,30 +455,62 @@ static int check_ready(tpdcu_ctx* c) {
 }
 
 static int finish_internal(tpdcu_ctx* c) {
-    if (!c->frame_valid && !c->frame_pending) return fail(TPDCU_ERR_STATE, "no frame has been rendered");
-    for (int attempt = 0; c->frame_pending; ++attempt) {
-        CK(cudaEventSynchronize(c->frame_done));
-        const uint32_t pairs = c->status[0].pairs_total;
-        bool again = false;
-        if (int r = frame_needs_rerender(c, c->status[0], &again)) return r;
-        if (!again) { c->frame_pending = false; c->frame_valid = true; break; }
-        if (attempt >= 4) return fail(TPDCU_ERR_STATE, "pair buffer kept overflowing");
-        CK(cudaStreamSynchronize(c->last_stream));
-        if (pairs > c->capacity)
-            if (int r = ensure_pairs(c, grown_capacity(pairs))) return r;
-        size_t pitch; uint8_t* out = out_ptr(c, &pitch);
-        if (int r = enqueue_frame(c, c->last_ubo, c->last_sh_degree, c->last_stream, out, pitch, 0)) return r;
-        CK(cudaEventRecord(c->frame_done, c->last_stream));
+    if (c->last_slot < 0 || (!c->frame_valid && !c->slots[c->last_slot].pending)) return fail(TPDCU_ERR_STATE, "no frame has been rendered");
+    // Earlier frames first, then the one the caller asks about. An earlier frame that overflowed is rendered again only if
+    // it went to a different target; on the same target it has been superseded and must not clobber the newer frame.
+    FrameSlot& newest = c->slots[c->last_slot];
+    for (int k = 1; k < MAX_SLOTS; ++k) {
+        FrameSlot& f = c->slots[(c->last_slot + k) % MAX_SLOTS];
+        if (!f.pending) continue;
+        if (f.out == newest.out) {
+            CK(cudaEventSynchronize(f.done));
+            const FrameStatus& st = c->status[f.status_index];
+            if (st.pairs_total > f.capacity) {
+                CK(cudaStreamSynchronize(f.stream));
+                if (int r = ensure_pairs(f, grown_capacity(st.pairs_total))) return r;
+            }
+            if (st.packed_overflow) c->packed_disabled = true;
+            f.pending = false;
+        } else if (int r = settle_slot(c, f)) {
+            return r;
+        }
     }
+    if (newest.pending)
+        if (int r = settle_slot(c, newest)) return r;
+    c->frame_valid = true;
     if (c->timing) {
         CK(cudaEventSynchronize(c->ev[6]));
         float ms;
+        // ev: 0 start | 1 after clear+setup | 2 after preprocess | 3 after hist+plan | 4 after passes | 5 after ranges | 6 after blend
         for (int k = 0; k < 6; ++k) { CK(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1])); c->stage_ms[k] = ms; }
-        // ev: 0 start | 1 after setup | 2 after preprocess | 3 after hist+plan | 4 after passes | 5 after ranges | 6 after blend
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[6]));
         c->stage_ms[6] = ms;
-        c->stage_ms[7] = (float)c->status[0].passes_run;
+        c->stage_ms[7] = (float)c->status[c->slots[c->last_slot].status_index].passes_run;
     }
+    return TPDCU_OK;
+}
+
+static FrameSlot& last(tpdcu_ctx* c) { return c->slots[c->last_slot]; }
+static const FrameStatus& last_status(tpdcu_ctx* c) { return c->status[last(c).status_index]; }
+
+// Pick the slot for the next frame; if it still holds an unsettled frame that overflowed, grow first.
+static int acquire_slot(tpdcu_ctx* c, FrameSlot** out) {
+    const int depth = c->timing ? 1 : c->frames_in_flight;
+    if (c->next_slot >= depth) c->next_slot = 0;
+    FrameSlot& f = c->slots[c->next_slot];
+    if (f.pending && cudaEventQuery(f.done) == cudaSuccess) {
+        // a superseded frame: its P still tells us how far to grow before starting the next one on this slot
+        const FrameStatus& st = c->status[f.status_index];
+        if (st.pairs_total > f.capacity) {
+            CK(cudaStreamSynchronize(f.stream));
+            if (int r = ensure_pairs(f, grown_capacity(st.pairs_total))) return r;
+        }
+        if (st.packed_overflow) c->packed_disabled = true;
+    }
+    cudaGetLastError();
+    c->last_slot = c->next_slot;
+    c->next_slot = (c->next_slot + 1) % depth;
+    *out = &f;
     return TPDCU_OK;
 }
 
@@ -429,17 +544,22 @@ int tpdcu_create(int device, tpdcu_ctx** out) {
         cudaError_t e_ = (call);                                                                    \
         if (e_ != cudaSuccess) return bail(fail(TPDCU_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_))); \
     } while (0)
-    CKB(cudaMalloc(&c->cam, sizeof(FrameCam)));
-    CKB(cudaMalloc(&c->plan, sizeof(SortPlan)));
-    CKB(cudaMemset(c->plan, 0, sizeof(SortPlan)));
-    CKB(cudaEventCreateWithFlags(&c->frame_done, cudaEventDisableTiming));
+    for (auto& f : c->slots) {
+        memset(&f.graph_sig, 0, sizeof(f.graph_sig));
+        CKB(cudaMalloc(&f.cam, sizeof(FrameCam)));
+        CKB(cudaMalloc(&f.plan, sizeof(SortPlan)));
+        CKB(cudaMemset(f.plan, 0, sizeof(SortPlan)));
+        CKB(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+        CKB(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
+        CKB(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    }
     CKB(cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
     for (auto& e : c->ev) CKB(cudaEventCreate(&e));
     for (auto& e : c->sort_ev) CKB(cudaEventCreate(&e));
 #undef CKB
-    memset(&c->graph_sig, 0, sizeof(c->graph_sig));
     if (cudaError_t e = init_sort_attributes()) return bail(fail(TPDCU_ERR_CUDA, std::string("init_sort_attributes: ") + cudaGetErrorString(e)));
-    if (int r = ensure_status(c, 1)) return bail(r);
+    if (int r = ensure_status(c, MAX_SLOTS)) return bail(r);
+    for (int k = 0; k < MAX_SLOTS; ++k) c->slots[k].status_index = (uint32_t)k;
     *out = c;
     return TPDCU_OK;
 }
@@ -449,14 +569,17 @@ void tpdcu_destroy(tpdcu_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     free_scene(c);
-    free_pairs(c);
-    cudaFree(c->cam); cudaFree(c->plan); cudaFree(c->zero_region); cudaFree(c->target);
-    cudaFree(c->unsorted_keys); cudaFree(c->unsorted_vals);
-    drop_graph(c);
+    for (auto& f : c->slots) {
+        free_slot_pairs(f);
+        cudaFree(f.cam); cudaFree(f.plan); cudaFree(f.zero_region); cudaFree(f.unsorted_keys); cudaFree(f.unsorted_vals);
+        if (f.stream) cudaStreamDestroy(f.stream);
+        if (f.fork) cudaEventDestroy(f.fork);
+        if (f.done) cudaEventDestroy(f.done);
+    }
+    cudaFree(c->target);
     if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
     if (c->ext_mem) cudaDestroyExternalMemory(c->ext_mem);
     if (c->status) cudaFreeHost(c->status);
-    if (c->frame_done) cudaEventDestroy(c->frame_done);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->sort_ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -471,20 +594,15 @@ int tpdcu_device_info(tpdcu_ctx* c, char* buf, size_t buf_bytes, int* sm_count) 
 
 static int upload_common(tpdcu_ctx* c, const void* d_recs, uint32_t n, const uint32_t* d_entity, uint32_t entity_count,
                          cudaStream_t s) {
-    // scene arrays
     free_scene(c);
     c->frame_valid = false;
+    c->last_slot = -1;
+    c->next_slot = 0;
+    for (auto& f : c->slots) f.pending = false;
     CK(cudaMalloc(&c->posop, (size_t)n * sizeof(float4)));
     CK(cudaMalloc(&c->cov_a, (size_t)n * sizeof(float4)));
     CK(cudaMalloc(&c->cov_b, (size_t)n * sizeof(float2)));
     CK(cudaMalloc(&c->sh, (size_t)n * SH_PLANES * sizeof(float4)));
-    CK(cudaMalloc(&c->geo, (size_t)n * sizeof(SplatGeo)));
-    CK(cudaMalloc(&c->color, (size_t)n * sizeof(float4)));
-    CK(cudaMalloc(&c->depth_radius, (size_t)n * sizeof(float2)));
-    CK(cudaMalloc(&c->offsets, ((size_t)n + 1) * sizeof(uint32_t)));
-    CK(cudaMalloc(&c->models, (size_t)entity_count * 16 * sizeof(float)));
-    CK(cudaMalloc(&c->vm, (size_t)entity_count * 16 * sizeof(float)));
-    CK(cudaMalloc(&c->pm, (size_t)entity_count * 16 * sizeof(float)));
     if (entity_count > 1) {
         CK(cudaMalloc(&c->entity, (size_t)n * sizeof(uint32_t)));
         if (d_entity) CK(cudaMemcpyAsync(c->entity, d_entity, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
@@ -495,7 +613,7 @@ static int upload_common(tpdcu_ctx* c, const void* d_recs, uint32_t n, const uin
     c->models_host.assign((size_t)entity_count * 16, 0.0f);  // identity (createBindlessTransformBuffer)
     for (uint32_t e = 0; e < entity_count; ++e)
         for (int k = 0; k < 4; ++k) c->models_host[(size_t)e * 16 + k * 5] = 1.0f;
-    c->models_dirty = true;
+    ++c->models_version;
     CompileLaunch cl{ reinterpret_cast<const float*>(d_recs), c->posop, c->cov_a, c->cov_b, c->sh, n };
     CK(launch_compile_scene(cl, s));
     return TPDCU_OK;
@@ -534,7 +652,10 @@ int tpdcu_upload_gaussians_device(tpdcu_ctx* c, const void* d_recs240, uint32_t 
     if (!d_recs240) return fail(TPDCU_ERR_INVALID, "d_recs240 is null");
     if (entity_count == 0) entity_count = 1;
     CK(cudaDeviceSynchronize());
-    return upload_common(c, d_recs240, n, d_entity_idx, entity_count, (cudaStream_t)stream);
+    const int r = upload_common(c, d_recs240, n, d_entity_idx, entity_count, (cudaStream_t)stream);
+    // the frame slots run on private streams: the compiled scene must be complete before any of them starts
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return r;
 }
 
 int tpdcu_set_transform(tpdcu_ctx* c, uint32_t entity, const float m[16]) {
@@ -542,7 +663,7 @@ int tpdcu_set_transform(tpdcu_ctx* c, uint32_t entity, const float m[16]) {
     if (c->n == 0) return fail(TPDCU_ERR_STATE, "no scene compiled");
     if (entity >= c->entity_count || !m) return fail(TPDCU_ERR_INVALID, "bad entity or matrix");
     memcpy(&c->models_host[(size_t)entity * 16], m, sizeof(float) * 16);
-    c->models_dirty = true;
+    ++c->models_version;
     return TPDCU_OK;
 }
 
@@ -550,9 +671,10 @@ int tpdcu_resize(tpdcu_ctx* c, uint32_t width, uint32_t height) {
     if (int r = check_ready(c)) return r;
     if (width == 0 || height == 0 || width > 65535u * TILE_PX || height > 65535u * TILE_PX)
         return fail(TPDCU_ERR_INVALID, "bad framebuffer size");
-    if (c->frame_pending) CK(cudaStreamSynchronize(c->last_stream));
-    c->frame_pending = false;
+    if (int r = sync_slots(c)) return r;
+    for (auto& f : c->slots) f.pending = false;
     c->frame_valid = false;
+    c->last_slot = -1;
     c->width = width;
     c->height = height;
     return ensure_target(c);
@@ -586,8 +708,7 @@ int tpdcu_bind_output_fd(tpdcu_ctx* c, int fd, size_t bytes) {
         cudaDestroyExternalMemory(mem);
         return fail(TPDCU_ERR_CUDA, std::string("cudaExternalMemoryGetMappedBuffer: ") + cudaGetErrorString(e));
     }
-    drop_graph(c);
-    if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
+    if (int r = sync_slots(c)) return r;
     if (c->ext_mem) cudaDestroyExternalMemory(c->ext_mem);
     c->ext_mem = mem;
     c->bound_out = reinterpret_cast<uint8_t*>(ptr);
@@ -595,29 +716,26 @@ int tpdcu_bind_output_fd(tpdcu_ctx* c, int fd, size_t bytes) {
     return TPDCU_OK;
 }
 
+static int raster_one(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cudaStream_t user, uint8_t* out, size_t pitch, int status_index) {
+    FrameSlot* f = nullptr;
+    if (int r = acquire_slot(c, &f)) return r;
+    memcpy(f->ubo, ubo, sizeof(f->ubo));
+    f->sh_degree = sh_degree;
+    f->out = out;
+    f->pitch = pitch;
+    f->user_stream = user;
+    f->status_index = status_index >= 0 ? (uint32_t)status_index : (uint32_t)(f - c->slots);
+    return enqueue_frame(c, *f);
+}
+
 int tpdcu_raster(tpdcu_ctx* c, const float camera_ubo[TPDCU_CAMERA_FLOATS], uint32_t sh_degree, void* stream) {
     if (int r = check_ready(c)) return r;
     if (!camera_ubo) return fail(TPDCU_ERR_INVALID, "camera_ubo is null");
     if (c->n == 0) return fail(TPDCU_ERR_STATE, "no scene compiled");
     if (c->width == 0) return fail(TPDCU_ERR_STATE, "tpdcu_resize has not been called");
-    cudaStream_t s = (cudaStream_t)stream;
-    // A still-pending frame that overflowed is simply superseded by this one; its P still tells us how
-    // far to grow before we start, if it has already landed.
-    if (c->frame_pending && cudaEventQuery(c->frame_done) == cudaSuccess && c->status[0].pairs_total > c->capacity) {
-        CK(cudaStreamSynchronize(c->last_stream));
-        if (int r = ensure_pairs(c, grown_capacity(c->status[0].pairs_total))) return r;
-    }
-    cudaGetLastError();
-    if (c->capacity == 0)
-        if (int r = ensure_pairs(c, SORT_TILE)) return r;
     size_t pitch; uint8_t* out = out_ptr(c, &pitch);
-    memcpy(c->last_ubo, camera_ubo, sizeof(c->last_ubo));
-    c->last_sh_degree = sh_degree;
-    c->last_stream = s;
-    if (int r = enqueue_frame(c, camera_ubo, sh_degree, s, out, pitch, 0)) return r;
-    CK(cudaEventRecord(c->frame_done, s));
-    c->frame_pending = true;
-    return TPDCU_OK;
+    c->frame_valid = false;
+    return raster_one(c, camera_ubo, sh_degree, (cudaStream_t)stream, out, pitch, -1);
 }
 
 int tpdcu_raster_views(tpdcu_ctx* c, const float* camera_ubos, uint32_t n_views, uint32_t sh_degree, void* d_frames,
@@ -629,43 +747,44 @@ int tpdcu_raster_views(tpdcu_ctx* c, const float* camera_ubos, uint32_t n_views,
     const size_t pitch = (size_t)c->width * 4;
     if (frame_stride_bytes < pitch * c->height) return fail(TPDCU_ERR_INVALID, "frame stride smaller than a frame");
     cudaStream_t s = (cudaStream_t)stream;
-    if (c->frame_pending) CK(cudaStreamSynchronize(c->last_stream));
-    c->frame_pending = false;
-    if (int r = ensure_status(c, n_views)) return r;
-    if (c->capacity == 0)
-        if (int r = ensure_pairs(c, SORT_TILE)) return r;
+    if (int r = sync_slots(c)) return r;
+    for (auto& f : c->slots) f.pending = false;
+    if (int r = ensure_status(c, MAX_SLOTS + n_views)) return r;
     std::vector<uint32_t> todo(n_views);
     for (uint32_t v = 0; v < n_views; ++v) todo[v] = v;
     const bool timing = c->timing;
     c->timing = false;  // per-stage events describe single frames only
+    c->frame_valid = false;
     int rc = TPDCU_OK;
     for (int attempt = 0; !todo.empty() && rc == TPDCU_OK; ++attempt) {
-        if (attempt >= 5) { rc = fail(TPDCU_ERR_STATE, "pair buffer kept overflowing"); break; }
+        if (attempt >= 6) { rc = fail(TPDCU_ERR_STATE, "frames kept overflowing their buffers"); break; }
         for (uint32_t v : todo) {
-            rc = enqueue_frame(c, camera_ubos + (size_t)v * TPDCU_CAMERA_FLOATS, sh_degree, s,
-                               reinterpret_cast<uint8_t*>(d_frames) + (size_t)v * frame_stride_bytes, pitch, v);
+            rc = raster_one(c, camera_ubos + (size_t)v * TPDCU_CAMERA_FLOATS, sh_degree, s,
+                            reinterpret_cast<uint8_t*>(d_frames) + (size_t)v * frame_stride_bytes, pitch, (int)(MAX_SLOTS + v));
             if (rc != TPDCU_OK) break;
         }
         if (rc != TPDCU_OK) break;
-        cudaError_t e = cudaStreamSynchronize(s);
+        cudaError_t e = cudaStreamSynchronize(s);  // s has waited for every frame of the batch
         if (e != cudaSuccess) { rc = fail(TPDCU_ERR_CUDA, std::string("batch sync: ") + cudaGetErrorString(e)); break; }
         std::vector<uint32_t> again;
         uint32_t max_pairs = 0;
         for (uint32_t v : todo) {
-            bool redo = false;
-            frame_needs_rerender(c, c->status[v], &redo);
-            if (redo) { again.push_back(v); max_pairs = std::max(max_pairs, c->status[v].pairs_total); }
+            const FrameStatus& st = c->status[MAX_SLOTS + v];
+            const bool overflow = st.pairs_total > c->ran_capacity[MAX_SLOTS + v];  // against the capacity it actually ran with
+            if (overflow || st.packed_overflow) {
+                again.push_back(v);
+                max_pairs = std::max(max_pairs, st.pairs_total);
+                if (st.packed_overflow && !overflow) c->packed_disabled = true;
+            }
         }
-        if (!again.empty() && max_pairs > c->capacity) rc = ensure_pairs(c, grown_capacity(max_pairs));
+        for (auto& f : c->slots) f.pending = false;
+        if (!again.empty())
+            for (int k = 0; k < c->frames_in_flight && rc == TPDCU_OK; ++k) rc = ensure_pairs(c->slots[k], grown_capacity(max_pairs));
         todo.swap(again);
     }
     c->timing = timing;
     if (rc != TPDCU_OK) return rc;
     // the last view rendered is what introspection sees
-    c->status[0] = c->status[n_views - 1];
-    memcpy(c->last_ubo, camera_ubos + (size_t)(n_views - 1) * TPDCU_CAMERA_FLOATS, sizeof(c->last_ubo));
-    c->last_sh_degree = sh_degree;
-    c->last_stream = s;
     c->frame_valid = true;
     return TPDCU_OK;
 }
@@ -673,7 +792,7 @@ int tpdcu_raster_views(tpdcu_ctx* c, const float* camera_ubos, uint32_t n_views,
 int tpdcu_finish(tpdcu_ctx* c, uint32_t* pairs) {
     if (int r = check_ready(c)) return r;
     if (int r = finish_internal(c)) return r;
-    if (pairs) *pairs = c->status[0].pairs_total;
+    if (pairs) *pairs = last_status(c).pairs_total;
     return TPDCU_OK;
 }
 
@@ -681,17 +800,17 @@ int tpdcu_read_frame(tpdcu_ctx* c, void* host_rgba8, size_t host_pitch_bytes) {
     if (int r = check_ready(c)) return r;
     if (!host_rgba8 || host_pitch_bytes < (size_t)c->width * 4) return fail(TPDCU_ERR_INVALID, "bad host buffer");
     if (int r = finish_internal(c)) return r;
-    size_t pitch; uint8_t* out = out_ptr(c, &pitch);
-    CK(cudaMemcpy2DAsync(host_rgba8, host_pitch_bytes, out, pitch, (size_t)c->width * 4, c->height, cudaMemcpyDeviceToHost, c->last_stream));
-    CK(cudaStreamSynchronize(c->last_stream));
+    FrameSlot& f = last(c);
+    CK(cudaMemcpy2DAsync(host_rgba8, host_pitch_bytes, f.out, f.pitch, (size_t)c->width * 4, c->height, cudaMemcpyDeviceToHost, f.stream));
+    CK(cudaStreamSynchronize(f.stream));
     return TPDCU_OK;
 }
 
 int tpdcu_get_counts(tpdcu_ctx* c, uint32_t* pairs, uint32_t* visible) {
     if (int r = check_ready(c)) return r;
     if (int r = finish_internal(c)) return r;
-    if (pairs) *pairs = c->status[0].pairs_total;
-    if (visible) *visible = c->status[0].visible;
+    if (pairs) *pairs = last_status(c).pairs_total;
+    if (visible) *visible = last_status(c).visible;
     return TPDCU_OK;
 }
 
@@ -700,11 +819,12 @@ int tpdcu_read_splats(tpdcu_ctx* c, void* host_splats48, uint32_t n) {
     if (!host_splats48 || n > c->n) return fail(TPDCU_ERR_INVALID, "bad splat read");
     if (int r = finish_internal(c)) return r;
     if (n == 0) return TPDCU_OK;
+    FrameSlot& f = last(c);
     void* tmp = nullptr;
     CK(cudaMalloc(&tmp, (size_t)n * TPDCU_SPLAT_BYTES));
-    cudaError_t e = launch_export_splats(SplatArrays{ c->geo, c->color, c->depth_radius, c->offsets }, n, tmp, c->last_stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(host_splats48, tmp, (size_t)n * TPDCU_SPLAT_BYTES, cudaMemcpyDeviceToHost, c->last_stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->last_stream);
+    cudaError_t e = launch_export_splats(SplatArrays{ f.geo, f.color, f.depth_radius, f.offsets }, n, tmp, f.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_splats48, tmp, (size_t)n * TPDCU_SPLAT_BYTES, cudaMemcpyDeviceToHost, f.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(f.stream);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(TPDCU_ERR_CUDA, std::string("read_splats: ") + cudaGetErrorString(e));
     return TPDCU_OK;
@@ -714,24 +834,25 @@ static int read_sorted(tpdcu_ctx* c, void* host, uint32_t count, bool want_keys)
     if (int r = check_ready(c)) return r;
     if (!host) return fail(TPDCU_ERR_INVALID, "host buffer is null");
     if (int r = finish_internal(c)) return r;
-    if (count > c->status[0].pairs_total) return fail(TPDCU_ERR_INVALID, "count exceeds the frame's pair count");
+    const FrameStatus& st = last_status(c);
+    FrameSlot& f = last(c);
+    if (count > st.pairs_total) return fail(TPDCU_ERR_INVALID, "count exceeds the frame's pair count");
     if (count == 0) return TPDCU_OK;
-    const FrameStatus& st = c->status[0];
     const void* src;
     if (st.packed) {
         // the frame's result is one array of packed words: expand it into the reference's (key, value) arrays in the
         // buffers the sort no longer needs
         SortLaunch so{};
-        so.keys[0] = c->keys[0]; so.keys[1] = c->keys[1]; so.plan = c->plan; so.sm_count = c->sm_count;
-        uint64_t* uk = c->keys[(st.final_sel & 1u) ^ 1u];
-        uint32_t* uv = c->vals[1];
-        CK(launch_sort_unpack(so, uk, uv, c->last_stream));
+        so.keys[0] = f.keys[0]; so.keys[1] = f.keys[1]; so.plan = f.plan; so.sm_count = c->sm_count;
+        uint64_t* uk = f.keys[(st.final_sel & 1u) ^ 1u];
+        uint32_t* uv = f.vals[1];
+        CK(launch_sort_unpack(so, uk, uv, f.stream));
         src = want_keys ? (const void*)uk : (const void*)uv;
     } else {
-        src = want_keys ? (const void*)c->keys[st.final_sel & 1u] : (const void*)c->vals[st.final_sel & 1u];
+        src = want_keys ? (const void*)f.keys[st.final_sel & 1u] : (const void*)f.vals[st.final_sel & 1u];
     }
-    CK(cudaMemcpyAsync(host, src, (size_t)count * (want_keys ? 8 : 4), cudaMemcpyDeviceToHost, c->last_stream));
-    CK(cudaStreamSynchronize(c->last_stream));
+    CK(cudaMemcpyAsync(host, src, (size_t)count * (want_keys ? 8 : 4), cudaMemcpyDeviceToHost, f.stream));
+    CK(cudaStreamSynchronize(f.stream));
     return TPDCU_OK;
 }
 
@@ -742,8 +863,9 @@ int tpdcu_read_ranges(tpdcu_ctx* c, uint32_t* host_ranges2, uint32_t tile_count)
     if (int r = check_ready(c)) return r;
     if (!host_ranges2 || tile_count > tiles_of(c)) return fail(TPDCU_ERR_INVALID, "bad range read");
     if (int r = finish_internal(c)) return r;
-    CK(cudaMemcpyAsync(host_ranges2, c->zero_region + c->off_ranges, (size_t)tile_count * 8, cudaMemcpyDeviceToHost, c->last_stream));
-    CK(cudaStreamSynchronize(c->last_stream));
+    FrameSlot& f = last(c);
+    CK(cudaMemcpyAsync(host_ranges2, f.zero_region + f.off_ranges, (size_t)tile_count * 8, cudaMemcpyDeviceToHost, f.stream));
+    CK(cudaStreamSynchronize(f.stream));
     return TPDCU_OK;
 }
 
@@ -755,18 +877,21 @@ int tpdcu_keep_unsorted(tpdcu_ctx* c, int enable) {
 
 int tpdcu_read_unsorted(tpdcu_ctx* c, uint64_t* host_keys, uint32_t* host_vals, uint32_t count) {
     if (int r = check_ready(c)) return r;
-    if (!c->keep_unsorted || !c->unsorted_keys) return fail(TPDCU_ERR_STATE, "tpdcu_keep_unsorted was not enabled for the last frame");
     if (int r = finish_internal(c)) return r;
-    if (count > c->status[0].pairs_total || count > c->unsorted_capacity) return fail(TPDCU_ERR_INVALID, "count exceeds the frame's pair count");
-    if (host_keys) CK(cudaMemcpyAsync(host_keys, c->unsorted_keys, (size_t)count * 8, cudaMemcpyDeviceToHost, c->last_stream));
-    if (host_vals) CK(cudaMemcpyAsync(host_vals, c->unsorted_vals, (size_t)count * 4, cudaMemcpyDeviceToHost, c->last_stream));
-    CK(cudaStreamSynchronize(c->last_stream));
+    FrameSlot& f = last(c);
+    if (!c->keep_unsorted || !f.unsorted_keys) return fail(TPDCU_ERR_STATE, "tpdcu_keep_unsorted was not enabled for the last frame");
+    if (count > last_status(c).pairs_total || count > f.unsorted_capacity) return fail(TPDCU_ERR_INVALID, "count exceeds the frame's pair count");
+    if (host_keys) CK(cudaMemcpyAsync(host_keys, f.unsorted_keys, (size_t)count * 8, cudaMemcpyDeviceToHost, f.stream));
+    if (host_vals) CK(cudaMemcpyAsync(host_vals, f.unsorted_vals, (size_t)count * 4, cudaMemcpyDeviceToHost, f.stream));
+    CK(cudaStreamSynchronize(f.stream));
     return TPDCU_OK;
 }
 
 int tpdcu_enable_stage_timing(tpdcu_ctx* c, int enable) {
     if (int r = check_ready(c)) return r;
+    CK(cudaDeviceSynchronize());  // timed frames run on the caller's stream, the others on the slots' streams: do not mix in flight
     c->timing = enable != 0;
+    c->next_slot = 0;
     return TPDCU_OK;
 }
 
@@ -783,7 +908,7 @@ int tpdcu_stage_times_ms(tpdcu_ctx* c, float times_ms[TPDCU_NUM_STAGES]) {
 int tpdcu_get_sort_info(tpdcu_ctx* c, uint32_t* packed, uint32_t* depth_bits, uint32_t* idx_bits, uint32_t* total_bits) {
     if (int r = check_ready(c)) return r;
     if (int r = finish_internal(c)) return r;
-    const FrameStatus& st = c->status[0];
+    const FrameStatus& st = last_status(c);
     if (packed) *packed = st.packed;
     if (depth_bits) *depth_bits = st.depth_bits;
     if (idx_bits) *idx_bits = st.idx_bits;
@@ -803,8 +928,8 @@ int tpdcu_set_graph_replay(tpdcu_ctx* c, int enable, uint32_t* captures, uint32_
     if (enable >= 0) {
         c->use_graph = enable != 0;
         if (!c->use_graph) {
-            if (c->frame_pending) CK(cudaStreamSynchronize(c->last_stream));
-            drop_graph(c);
+            if (int r = sync_slots(c)) return r;
+            for (auto& f : c->slots) drop_graph(f);
         }
     }
     if (captures) *captures = c->graph_captures;
@@ -812,17 +937,32 @@ int tpdcu_set_graph_replay(tpdcu_ctx* c, int enable, uint32_t* captures, uint32_
     return TPDCU_OK;
 }
 
+int tpdcu_set_frames_in_flight(tpdcu_ctx* c, int frames) {
+    if (int r = check_ready(c)) return r;
+    if (frames < 1 || frames > MAX_SLOTS) return fail(TPDCU_ERR_INVALID, "frames in flight must be 1 or 2");
+    if (c->last_slot >= 0)
+        if (int r = finish_internal(c)) return r;
+    if (int r = sync_slots(c)) return r;
+    c->frames_in_flight = frames;
+    c->next_slot = 0;
+    return TPDCU_OK;
+}
+
 int tpdcu_get_capacity(tpdcu_ctx* c, uint32_t* capacity_pairs) {
     if (int r = check_ready(c)) return r;
-    if (capacity_pairs) *capacity_pairs = c->capacity;
+    uint32_t cap = 0;
+    for (const auto& f : c->slots) cap = std::max(cap, f.capacity);  // every frame slot grows on its own; report the largest
+    if (capacity_pairs) *capacity_pairs = cap;
     return TPDCU_OK;
 }
 
 int tpdcu_reserve_pairs(tpdcu_ctx* c, uint32_t capacity_pairs) {
     if (int r = check_ready(c)) return r;
-    if (c->frame_pending) { if (int r = finish_internal(c)) return r; }
+    if (int r = sync_slots(c)) return r;
     CK(cudaDeviceSynchronize());
-    return ensure_pairs(c, capacity_pairs);
+    for (int k = 0; k < c->frames_in_flight; ++k)
+        if (int r = ensure_pairs(c->slots[k], capacity_pairs)) return r;
+    return TPDCU_OK;
 }
 
 int tpdcu_sort_pairs_device(tpdcu_ctx* c, uint64_t* d_keys, uint32_t* d_vals, uint32_t n, uint32_t end_bit, void* stream) {
@@ -831,38 +971,43 @@ int tpdcu_sort_pairs_device(tpdcu_ctx* c, uint64_t* d_keys, uint32_t* d_vals, ui
     if (end_bit > 64) return fail(TPDCU_ERR_INVALID, "end_bit > 64");
     if (n >= (1u << 30)) return fail(TPDCU_ERR_INVALID, "n must be below 2^30");
     cudaStream_t s = (cudaStream_t)stream;
-    if (c->frame_pending) { if (int r = finish_internal(c)) return r; }
-    c->frame_valid = false;  // the pair buffers are about to be reused
-    if (n > c->capacity) {
+    if (int r = sync_slots(c)) return r;
+    for (auto& f : c->slots) f.pending = false;
+    c->frame_valid = false;  // slot 0's pair buffers are about to be reused
+    c->last_slot = -1;
+    FrameSlot& f = c->slots[0];
+    if (n > f.capacity) {
         CK(cudaDeviceSynchronize());
-        if (int r = ensure_pairs(c, n)) return r;
+        if (int r = ensure_pairs(f, n)) return r;
     }
-    if (c->capacity == 0)
-        if (int r = ensure_pairs(c, SORT_TILE)) return r;
-    if (int r = ensure_zero_region(c, SORT_MAX_PASSES)) return r;
-    CK(cudaMemsetAsync(c->zero_region, 0, c->zero_bytes, s));
+    if (f.capacity == 0)
+        if (int r = ensure_pairs(f, SORT_TILE)) return r;
+    if (int r = ensure_zero_region(c, f)) return r;
+    CK(cudaMemsetAsync(f.zero_region, 0, f.zero_bytes, s));
     if (n) {
-        CK(cudaMemcpyAsync(c->keys[0], d_keys, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
-        CK(cudaMemcpyAsync(c->vals[0], d_vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(f.keys[0], d_keys, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(f.vals[0], d_vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
     }
     SortLaunch so{};
-    so.keys[0] = c->keys[0]; so.keys[1] = c->keys[1]; so.vals[0] = c->vals[0]; so.vals[1] = c->vals[1];
-    so.ctl = reinterpret_cast<FrameCtl*>(c->zero_region); so.plan = c->plan;
-    so.lookback = reinterpret_cast<uint32_t*>(c->zero_region + c->off_lookback);
-    so.capacity = c->capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
+    so.keys[0] = f.keys[0]; so.keys[1] = f.keys[1]; so.vals[0] = f.vals[0]; so.vals[1] = f.vals[1];
+    so.ctl = reinterpret_cast<FrameCtl*>(f.zero_region); so.plan = f.plan;
+    so.lookback = reinterpret_cast<uint32_t*>(f.zero_region + f.off_lookback);
+    so.capacity = f.capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
     CK(cudaEventRecord(c->sort_ev[0], s));
     CK(launch_sort(so, n, s, nullptr));
     CK(cudaEventRecord(c->sort_ev[1], s));
     CK(launch_sort_copy_result(so, d_keys, d_vals, n, s));
-    CK(cudaMemcpyAsync(&c->status[0].n, c->plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    c->last_stream = s;
+    CK(cudaMemcpyAsync(&c->status[0].n, f.plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    c->sort_stream = s;
+    c->sort_done = true;
     return TPDCU_OK;
 }
 
 int tpdcu_sort_last_ms(tpdcu_ctx* c, float* ms, uint32_t* passes_run) {
     if (int r = check_ready(c)) return r;
+    if (!c->sort_done) return fail(TPDCU_ERR_STATE, "tpdcu_sort_pairs_device has not been called");
     CK(cudaEventSynchronize(c->sort_ev[1]));
-    CK(cudaStreamSynchronize(c->last_stream));
+    CK(cudaStreamSynchronize(c->sort_stream));
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, c->sort_ev[0], c->sort_ev[1]));
     if (ms) *ms = t;

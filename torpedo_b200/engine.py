@@ -306,6 +306,9 @@ class GaussianEngine:
         check(tpdcu().tpdcu_set_graph_replay(self._ctx, enable, C.byref(cap), C.byref(lau)))
         return cap.value, lau.value
 
+    def set_frames_in_flight(self, frames: int) -> None:
+        check(tpdcu().tpdcu_set_frames_in_flight(self._ctx, frames))
+
     def capacity(self) -> int:
         c = u32(0)
         check(tpdcu().tpdcu_get_capacity(self._ctx, C.byref(c)))
