@@ -365,6 +365,7 @@ def test_two_frames_in_flight_match_serial_rendering(E, oracle):
     for k, u in enumerate(ubos):
         check(tpdcu().tpdcu_bind_output_device_ptr(eng.ctx, frames[k].data_ptr(), w * 4))
         eng.raster_ubo(u, 3, stream)
+    eng.finish()  # the one host-side check: the second slot's buffers were still small, its first frame is repeated here
     torch.cuda.synchronize()
     out = frames.cpu().numpy()
     for k in range(7):

@@ -49,6 +49,20 @@ struct FrameStatus {  // pinned host mirror of what a frame reports back
 static_assert(offsetof(SortPlan, packed_overflow) == 9 * sizeof(uint32_t), "FrameStatus mirrors the head of SortPlan");
 
 constexpr int MAX_SLOTS = 2;
+constexpr uint32_t TICKET_RING = 256;  // frames that may be enqueued between two host-side checks (tpdcu_finish & co.)
+
+// What it takes to render a frame again: kept for every frame enqueued since the last check, because P is only looked at
+// lazily (no mid-frame read-back) and an overflowing frame has to be repeated after its buffers have grown.
+struct FrameTicket {
+    float ubo[TPDCU_CAMERA_FLOATS];
+    uint32_t sh_degree;
+    uint8_t* out;
+    size_t pitch;
+    cudaStream_t user_stream;
+    uint32_t ran_capacity;  // pair capacity of the slot it ran on
+    uint32_t status;        // index into the pinned status ring
+    int slot;
+};
 
 struct GraphSig {  // everything a captured frame bakes in
     const void* zero_region; size_t zero_bytes; const void* keys0; const void* keys1; const void* geo; const void* posop;
@@ -89,14 +103,7 @@ struct FrameSlot {
     bool graph_valid = false;
     GraphSig graph_sig;
     cudaGraphExec_t graph_exec = nullptr;
-    // the frame it holds
-    bool pending = false;
-    float ubo[TPDCU_CAMERA_FLOATS];
-    uint32_t sh_degree = 3;
-    uint8_t* out = nullptr;
-    size_t pitch = 0;
-    cudaStream_t user_stream = nullptr;
-    uint32_t status_index = 0;
+    bool busy = false;  // something has been enqueued on `stream` since it was last waited for
 };
 
 struct tpdcu_ctx {
@@ -117,8 +124,6 @@ struct tpdcu_ctx {
     FrameSlot slots[MAX_SLOTS];
     int frames_in_flight = 2;
     int next_slot = 0;
-    int last_slot = -1;  // slot of the most recent frame (what finish / read_* / introspection refer to)
-    bool frame_valid = false;
 
     uint32_t packed_word_bits = 64;
     bool packed_disabled = false;  // a frame whose depth range did not fit packed sort words switches the context to pair mode
@@ -135,9 +140,11 @@ struct tpdcu_ctx {
     size_t bound_pitch = 0;
     cudaExternalMemory_t ext_mem = nullptr;
 
-    FrameStatus* status = nullptr;  // pinned, status_slots entries; entries [0, MAX_SLOTS) belong to the frame slots
-    uint32_t status_slots = 0;
-    std::vector<uint32_t> ran_capacity;  // per status entry: the pair capacity the frame was enqueued with
+    FrameStatus* status = nullptr;       // pinned ring, TICKET_RING entries
+    std::vector<FrameTicket> unchecked;  // frames enqueued since the last host-side check, oldest first
+    uint32_t next_status = 0;
+    FrameTicket newest{};                // the most recent frame: what finish / read_* / introspection refer to
+    bool have_newest = false;
 
     bool timing = false;
     cudaEvent_t ev[7] = {};
@@ -248,18 +255,10 @@ static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f) {
     return TPDCU_OK;
 }
 
-static int ensure_status(tpdcu_ctx* c, uint32_t slots) {
-    if (slots <= c->status_slots) return TPDCU_OK;
-    FrameStatus* fresh = nullptr;
-    CK(cudaMallocHost(&fresh, sizeof(FrameStatus) * slots));
-    memset(fresh, 0, sizeof(FrameStatus) * slots);
-    if (c->status) {
-        memcpy(fresh, c->status, sizeof(FrameStatus) * c->status_slots);
-        cudaFreeHost(c->status);
-    }
-    c->status = fresh;
-    c->status_slots = slots;
-    c->ran_capacity.resize(slots, 0u);
+static int ensure_status(tpdcu_ctx* c) {
+    if (c->status) return TPDCU_OK;
+    CK(cudaMallocHost(&c->status, sizeof(FrameStatus) * TICKET_RING));
+    memset(c->status, 0, sizeof(FrameStatus) * TICKET_RING);
     return TPDCU_OK;
 }
 
@@ -304,17 +303,16 @@ static int enqueue_middle(tpdcu_ctx* c, FrameSlot& f, const FrameLaunch& l, cuda
     return TPDCU_OK;
 }
 
-// Enqueue the frame described by the slot (f.ubo, f.sh_degree, f.out, f.pitch, f.user_stream, f.status_index).
-// No host synchronisation. With stage timing everything runs on the caller's stream; otherwise the front of the frame runs
+// Enqueue the frame described by the ticket on slot `f`. No host synchronisation. With stage timing everything runs on the caller's stream; otherwise the front of the frame runs
 // on the slot's stream unordered with the caller's stream, the blend waits for the caller's stream (it writes the target)
 // and the caller's stream waits for the frame.
-static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f) {
+static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     if (int r = ensure_slot_scene(c, f)) return r;
     if (f.capacity == 0)
         if (int r = ensure_pairs(f, SORT_TILE)) return r;
     if (int r = ensure_zero_region(c, f)) return r;
     const bool t = c->timing;
-    cudaStream_t user = f.user_stream;
+    cudaStream_t user = tk.user_stream;
     cudaStream_t s = t ? user : f.stream;
 
     if (f.models_version != c->models_version) {
@@ -341,7 +339,7 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f) {
     p.out = SplatArrays{ f.geo, f.color, f.depth_radius, f.offsets };
     p.keys = f.keys[0]; p.vals = f.vals[0];
     p.capacity = f.capacity;
-    p.width = c->width; p.height = c->height; p.sh_degree = std::min(f.sh_degree, 3u);  // GaussianEngine.cpp:366-370
+    p.width = c->width; p.height = c->height; p.sh_degree = std::min(tk.sh_degree, 3u);  // GaussianEngine.cpp:366-370
 
     SortLaunch& so = l.sort;
     so.keys[0] = f.keys[0]; so.keys[1] = f.keys[1]; so.vals[0] = f.vals[0]; so.vals[1] = f.vals[1];
@@ -355,11 +353,11 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f) {
     ra.keys[0] = f.keys[0]; ra.keys[1] = f.keys[1]; ra.vals[0] = f.vals[0]; ra.vals[1] = f.vals[1];
     ra.plan = f.plan; ra.geo = f.geo; ra.color = f.color;
     ra.ranges = reinterpret_cast<uint32_t*>(f.zero_region + f.off_ranges);
-    ra.out = f.out; ra.pitch = f.pitch; ra.capacity = f.capacity; ra.width = c->width; ra.height = c->height;
+    ra.out = tk.out; ra.pitch = tk.pitch; ra.capacity = f.capacity; ra.width = c->width; ra.height = c->height;
 
     if (t) CK(cudaEventRecord(c->ev[0], s));
     CameraUbo cu;
-    memcpy(cu.f, f.ubo, sizeof(cu.f));  // by-value kernel argument: no per-frame H2D copy (updateCameraBuffer, :764-775)
+    memcpy(cu.f, tk.ubo, sizeof(cu.f));  // by-value kernel argument: no per-frame H2D copy (updateCameraBuffer, :764-775)
     CK(launch_setup(p, cu, s));
 
     bool replayed = false;
@@ -408,38 +406,19 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f) {
     CK(launch_blend(ra, s));
     if (t) CK(cudaEventRecord(c->ev[6], s));
 
-    FrameStatus* st = &c->status[f.status_index];
+    FrameStatus* st = &c->status[tk.status];
     CK(cudaMemcpyAsync(&st->pairs_total, &ctl->pairs_total, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&st->n, f.plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(f.done, s));
     if (!t) CK(cudaStreamWaitEvent(user, f.done, 0));
-    c->ran_capacity[f.status_index] = f.capacity;
-    f.pending = true;
+    tk.ran_capacity = f.capacity;
+    f.busy = true;
     return TPDCU_OK;
 }
 
 static uint32_t grown_capacity(uint32_t pairs) {
     const uint64_t want = (uint64_t)pairs + pairs / 8 + SORT_TILE;  // 12.5 % head-room against view changes
     return (uint32_t)std::min<uint64_t>(want, 0xffffffffull - 2 * SORT_TILE);
-}
-
-// Wait for the slot's frame; if it overflowed the pair buffers or the packed word, fix the cause and render it again.
-static int settle_slot(tpdcu_ctx* c, FrameSlot& f) {
-    for (int attempt = 0; f.pending; ++attempt) {
-        CK(cudaEventSynchronize(f.done));
-        const FrameStatus& st = c->status[f.status_index];
-        const bool grow = st.pairs_total > f.capacity;
-        const bool unpack = !grow && st.packed_overflow;
-        if (!grow && !unpack) { f.pending = false; break; }
-        if (attempt >= 5) return fail(TPDCU_ERR_STATE, "frame kept overflowing its buffers");
-        if (unpack) c->packed_disabled = true;
-        CK(cudaStreamSynchronize(f.stream));
-        CK(cudaStreamSynchronize(f.user_stream));
-        if (grow)
-            if (int r = ensure_pairs(f, grown_capacity(st.pairs_total))) return r;
-        if (int r = enqueue_frame(c, f)) return r;
-    }
-    return TPDCU_OK;
 }
 
 static uint8_t* out_ptr(tpdcu_ctx* c, size_t* pitch) {
@@ -454,30 +433,74 @@ static int check_ready(tpdcu_ctx* c) {
     return TPDCU_OK;
 }
 
-static int finish_internal(tpdcu_ctx* c) {
-    if (c->last_slot < 0 || (!c->frame_valid && !c->slots[c->last_slot].pending)) return fail(TPDCU_ERR_STATE, "no frame has been rendered");
-    // Earlier frames first, then the one the caller asks about. An earlier frame that overflowed is rendered again only if
-    // it went to a different target; on the same target it has been superseded and must not clobber the newer frame.
-    FrameSlot& newest = c->slots[c->last_slot];
-    for (int k = 1; k < MAX_SLOTS; ++k) {
-        FrameSlot& f = c->slots[(c->last_slot + k) % MAX_SLOTS];
-        if (!f.pending) continue;
-        if (f.out == newest.out) {
+static int wait_slots(tpdcu_ctx* c) {
+    for (auto& f : c->slots)
+        if (f.busy) {
             CK(cudaEventSynchronize(f.done));
-            const FrameStatus& st = c->status[f.status_index];
-            if (st.pairs_total > f.capacity) {
-                CK(cudaStreamSynchronize(f.stream));
-                if (int r = ensure_pairs(f, grown_capacity(st.pairs_total))) return r;
-            }
-            if (st.packed_overflow) c->packed_disabled = true;
-            f.pending = false;
-        } else if (int r = settle_slot(c, f)) {
-            return r;
+            f.busy = false;
+        }
+    return TPDCU_OK;
+}
+
+static int finish_internal(tpdcu_ctx* c);
+
+// Enqueue one frame on the next slot and remember how to repeat it.
+static int raster_one(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cudaStream_t user, uint8_t* out, size_t pitch) {
+    if (c->unchecked.size() >= TICKET_RING - 2)  // the status ring is full: look at what is pending before going on
+        if (int r = finish_internal(c)) return r;
+    const int depth = c->timing ? 1 : c->frames_in_flight;
+    if (c->next_slot >= depth) c->next_slot = 0;
+    const int slot = c->next_slot;
+    c->next_slot = (c->next_slot + 1) % depth;
+    FrameTicket tk{};
+    memcpy(tk.ubo, ubo, sizeof(tk.ubo));
+    tk.sh_degree = sh_degree;
+    tk.out = out;
+    tk.pitch = pitch;
+    tk.user_stream = user;
+    tk.slot = slot;
+    tk.status = c->next_status;
+    c->next_status = (c->next_status + 1) % (TICKET_RING - 1);  // the last entry belongs to the standalone sort
+    if (int r = enqueue_frame(c, c->slots[slot], tk)) return r;
+    c->unchecked.push_back(tk);
+    c->newest = tk;
+    c->have_newest = true;
+    return TPDCU_OK;
+}
+
+// Host-side check of everything enqueued since the last check: wait for the frames, and render again (after growing the
+// buffers / leaving packed mode) those that overflowed — unless a later frame went to the same target, in which case the
+// frame has been superseded and repeating it would clobber the newer image.
+static int finish_internal(tpdcu_ctx* c) {
+    if (!c->have_newest) return fail(TPDCU_ERR_STATE, "no frame has been rendered");
+    for (int attempt = 0; !c->unchecked.empty(); ++attempt) {
+        if (attempt >= 6) return fail(TPDCU_ERR_STATE, "frames kept overflowing their buffers");
+        if (int r = wait_slots(c)) return r;
+        std::vector<FrameTicket> pending;
+        pending.swap(c->unchecked);
+        std::vector<FrameTicket> redo;
+        uint32_t max_pairs = 0;
+        for (size_t i = 0; i < pending.size(); ++i) {
+            const FrameTicket& tk = pending[i];
+            const FrameStatus& st = c->status[tk.status];
+            const bool overflow = st.pairs_total > tk.ran_capacity;
+            if (!overflow && !st.packed_overflow) continue;
+            if (overflow) max_pairs = std::max(max_pairs, st.pairs_total);
+            else c->packed_disabled = true;
+            bool superseded = false;
+            for (size_t j = i + 1; j < pending.size() && !superseded; ++j) superseded = pending[j].out == tk.out;
+            if (!superseded) redo.push_back(tk);
+        }
+        if (max_pairs)
+            for (int k = 0; k < MAX_SLOTS; ++k)
+                if (c->slots[k].capacity || k < c->frames_in_flight)
+                    if (int r = ensure_pairs(c->slots[k], grown_capacity(max_pairs))) return r;
+        for (const FrameTicket& tk : redo) {
+            CK(cudaStreamSynchronize(tk.user_stream));
+            if (int r = raster_one(c, tk.ubo, tk.sh_degree, tk.user_stream, tk.out, tk.pitch)) return r;
         }
     }
-    if (newest.pending)
-        if (int r = settle_slot(c, newest)) return r;
-    c->frame_valid = true;
+    if (int r = wait_slots(c)) return r;
     if (c->timing) {
         CK(cudaEventSynchronize(c->ev[6]));
         float ms;
@@ -485,33 +508,18 @@ static int finish_internal(tpdcu_ctx* c) {
         for (int k = 0; k < 6; ++k) { CK(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1])); c->stage_ms[k] = ms; }
         CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[6]));
         c->stage_ms[6] = ms;
-        c->stage_ms[7] = (float)c->status[c->slots[c->last_slot].status_index].passes_run;
+        c->stage_ms[7] = (float)c->status[c->newest.status].passes_run;
     }
     return TPDCU_OK;
 }
 
-static FrameSlot& last(tpdcu_ctx* c) { return c->slots[c->last_slot]; }
-static const FrameStatus& last_status(tpdcu_ctx* c) { return c->status[last(c).status_index]; }
+static FrameSlot& last(tpdcu_ctx* c) { return c->slots[c->newest.slot]; }
+static const FrameStatus& last_status(tpdcu_ctx* c) { return c->status[c->newest.status]; }
 
-// Pick the slot for the next frame; if it still holds an unsettled frame that overflowed, grow first.
-static int acquire_slot(tpdcu_ctx* c, FrameSlot** out) {
-    const int depth = c->timing ? 1 : c->frames_in_flight;
-    if (c->next_slot >= depth) c->next_slot = 0;
-    FrameSlot& f = c->slots[c->next_slot];
-    if (f.pending && cudaEventQuery(f.done) == cudaSuccess) {
-        // a superseded frame: its P still tells us how far to grow before starting the next one on this slot
-        const FrameStatus& st = c->status[f.status_index];
-        if (st.pairs_total > f.capacity) {
-            CK(cudaStreamSynchronize(f.stream));
-            if (int r = ensure_pairs(f, grown_capacity(st.pairs_total))) return r;
-        }
-        if (st.packed_overflow) c->packed_disabled = true;
-    }
-    cudaGetLastError();
-    c->last_slot = c->next_slot;
-    c->next_slot = (c->next_slot + 1) % depth;
-    *out = &f;
-    return TPDCU_OK;
+static void forget_frames(tpdcu_ctx* c) {
+    c->unchecked.clear();
+    c->have_newest = false;
+    c->next_slot = 0;
 }
 
 // ================================================================================================
@@ -558,8 +566,7 @@ int tpdcu_create(int device, tpdcu_ctx** out) {
     for (auto& e : c->sort_ev) CKB(cudaEventCreate(&e));
 #undef CKB
     if (cudaError_t e = init_sort_attributes()) return bail(fail(TPDCU_ERR_CUDA, std::string("init_sort_attributes: ") + cudaGetErrorString(e)));
-    if (int r = ensure_status(c, MAX_SLOTS)) return bail(r);
-    for (int k = 0; k < MAX_SLOTS; ++k) c->slots[k].status_index = (uint32_t)k;
+    if (int r = ensure_status(c)) return bail(r);
     *out = c;
     return TPDCU_OK;
 }
@@ -595,10 +602,7 @@ int tpdcu_device_info(tpdcu_ctx* c, char* buf, size_t buf_bytes, int* sm_count) 
 static int upload_common(tpdcu_ctx* c, const void* d_recs, uint32_t n, const uint32_t* d_entity, uint32_t entity_count,
                          cudaStream_t s) {
     free_scene(c);
-    c->frame_valid = false;
-    c->last_slot = -1;
-    c->next_slot = 0;
-    for (auto& f : c->slots) f.pending = false;
+    forget_frames(c);
     CK(cudaMalloc(&c->posop, (size_t)n * sizeof(float4)));
     CK(cudaMalloc(&c->cov_a, (size_t)n * sizeof(float4)));
     CK(cudaMalloc(&c->cov_b, (size_t)n * sizeof(float2)));
@@ -672,9 +676,7 @@ int tpdcu_resize(tpdcu_ctx* c, uint32_t width, uint32_t height) {
     if (width == 0 || height == 0 || width > 65535u * TILE_PX || height > 65535u * TILE_PX)
         return fail(TPDCU_ERR_INVALID, "bad framebuffer size");
     if (int r = sync_slots(c)) return r;
-    for (auto& f : c->slots) f.pending = false;
-    c->frame_valid = false;
-    c->last_slot = -1;
+    forget_frames(c);
     c->width = width;
     c->height = height;
     return ensure_target(c);
@@ -716,26 +718,13 @@ int tpdcu_bind_output_fd(tpdcu_ctx* c, int fd, size_t bytes) {
     return TPDCU_OK;
 }
 
-static int raster_one(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cudaStream_t user, uint8_t* out, size_t pitch, int status_index) {
-    FrameSlot* f = nullptr;
-    if (int r = acquire_slot(c, &f)) return r;
-    memcpy(f->ubo, ubo, sizeof(f->ubo));
-    f->sh_degree = sh_degree;
-    f->out = out;
-    f->pitch = pitch;
-    f->user_stream = user;
-    f->status_index = status_index >= 0 ? (uint32_t)status_index : (uint32_t)(f - c->slots);
-    return enqueue_frame(c, *f);
-}
-
 int tpdcu_raster(tpdcu_ctx* c, const float camera_ubo[TPDCU_CAMERA_FLOATS], uint32_t sh_degree, void* stream) {
     if (int r = check_ready(c)) return r;
     if (!camera_ubo) return fail(TPDCU_ERR_INVALID, "camera_ubo is null");
     if (c->n == 0) return fail(TPDCU_ERR_STATE, "no scene compiled");
     if (c->width == 0) return fail(TPDCU_ERR_STATE, "tpdcu_resize has not been called");
     size_t pitch; uint8_t* out = out_ptr(c, &pitch);
-    c->frame_valid = false;
-    return raster_one(c, camera_ubo, sh_degree, (cudaStream_t)stream, out, pitch, -1);
+    return raster_one(c, camera_ubo, sh_degree, (cudaStream_t)stream, out, pitch);
 }
 
 int tpdcu_raster_views(tpdcu_ctx* c, const float* camera_ubos, uint32_t n_views, uint32_t sh_degree, void* d_frames,
@@ -746,47 +735,20 @@ int tpdcu_raster_views(tpdcu_ctx* c, const float* camera_ubos, uint32_t n_views,
     if (c->width == 0) return fail(TPDCU_ERR_STATE, "tpdcu_resize has not been called");
     const size_t pitch = (size_t)c->width * 4;
     if (frame_stride_bytes < pitch * c->height) return fail(TPDCU_ERR_INVALID, "frame stride smaller than a frame");
-    cudaStream_t s = (cudaStream_t)stream;
-    if (int r = sync_slots(c)) return r;
-    for (auto& f : c->slots) f.pending = false;
-    if (int r = ensure_status(c, MAX_SLOTS + n_views)) return r;
-    std::vector<uint32_t> todo(n_views);
-    for (uint32_t v = 0; v < n_views; ++v) todo[v] = v;
     const bool timing = c->timing;
+    if (timing) CK(cudaDeviceSynchronize());
     c->timing = false;  // per-stage events describe single frames only
-    c->frame_valid = false;
     int rc = TPDCU_OK;
-    for (int attempt = 0; !todo.empty() && rc == TPDCU_OK; ++attempt) {
-        if (attempt >= 6) { rc = fail(TPDCU_ERR_STATE, "frames kept overflowing their buffers"); break; }
-        for (uint32_t v : todo) {
-            rc = raster_one(c, camera_ubos + (size_t)v * TPDCU_CAMERA_FLOATS, sh_degree, s,
-                            reinterpret_cast<uint8_t*>(d_frames) + (size_t)v * frame_stride_bytes, pitch, (int)(MAX_SLOTS + v));
-            if (rc != TPDCU_OK) break;
-        }
-        if (rc != TPDCU_OK) break;
-        cudaError_t e = cudaStreamSynchronize(s);  // s has waited for every frame of the batch
-        if (e != cudaSuccess) { rc = fail(TPDCU_ERR_CUDA, std::string("batch sync: ") + cudaGetErrorString(e)); break; }
-        std::vector<uint32_t> again;
-        uint32_t max_pairs = 0;
-        for (uint32_t v : todo) {
-            const FrameStatus& st = c->status[MAX_SLOTS + v];
-            const bool overflow = st.pairs_total > c->ran_capacity[MAX_SLOTS + v];  // against the capacity it actually ran with
-            if (overflow || st.packed_overflow) {
-                again.push_back(v);
-                max_pairs = std::max(max_pairs, st.pairs_total);
-                if (st.packed_overflow && !overflow) c->packed_disabled = true;
-            }
-        }
-        for (auto& f : c->slots) f.pending = false;
-        if (!again.empty())
-            for (int k = 0; k < c->frames_in_flight && rc == TPDCU_OK; ++k) rc = ensure_pairs(c->slots[k], grown_capacity(max_pairs));
-        todo.swap(again);
+    for (uint32_t v = 0; v < n_views && rc == TPDCU_OK; ++v)
+        rc = raster_one(c, camera_ubos + (size_t)v * TPDCU_CAMERA_FLOATS, sh_degree, (cudaStream_t)stream,
+                        reinterpret_cast<uint8_t*>(d_frames) + (size_t)v * frame_stride_bytes, pitch);
+    if (rc == TPDCU_OK) rc = finish_internal(c);  // every view has its own target: each one that overflowed is rendered again
+    if (rc == TPDCU_OK) {
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) rc = fail(TPDCU_ERR_CUDA, std::string("batch sync: ") + cudaGetErrorString(e));
     }
     c->timing = timing;
-    if (rc != TPDCU_OK) return rc;
-    // the last view rendered is what introspection sees
-    c->frame_valid = true;
-    return TPDCU_OK;
+    return rc;
 }
 
 int tpdcu_finish(tpdcu_ctx* c, uint32_t* pairs) {
@@ -801,7 +763,7 @@ int tpdcu_read_frame(tpdcu_ctx* c, void* host_rgba8, size_t host_pitch_bytes) {
     if (!host_rgba8 || host_pitch_bytes < (size_t)c->width * 4) return fail(TPDCU_ERR_INVALID, "bad host buffer");
     if (int r = finish_internal(c)) return r;
     FrameSlot& f = last(c);
-    CK(cudaMemcpy2DAsync(host_rgba8, host_pitch_bytes, f.out, f.pitch, (size_t)c->width * 4, c->height, cudaMemcpyDeviceToHost, f.stream));
+    CK(cudaMemcpy2DAsync(host_rgba8, host_pitch_bytes, c->newest.out, c->newest.pitch, (size_t)c->width * 4, c->height, cudaMemcpyDeviceToHost, f.stream));
     CK(cudaStreamSynchronize(f.stream));
     return TPDCU_OK;
 }
@@ -940,7 +902,7 @@ int tpdcu_set_graph_replay(tpdcu_ctx* c, int enable, uint32_t* captures, uint32_
 int tpdcu_set_frames_in_flight(tpdcu_ctx* c, int frames) {
     if (int r = check_ready(c)) return r;
     if (frames < 1 || frames > MAX_SLOTS) return fail(TPDCU_ERR_INVALID, "frames in flight must be 1 or 2");
-    if (c->last_slot >= 0)
+    if (c->have_newest)
         if (int r = finish_internal(c)) return r;
     if (int r = sync_slots(c)) return r;
     c->frames_in_flight = frames;
@@ -972,9 +934,7 @@ int tpdcu_sort_pairs_device(tpdcu_ctx* c, uint64_t* d_keys, uint32_t* d_vals, ui
     if (n >= (1u << 30)) return fail(TPDCU_ERR_INVALID, "n must be below 2^30");
     cudaStream_t s = (cudaStream_t)stream;
     if (int r = sync_slots(c)) return r;
-    for (auto& f : c->slots) f.pending = false;
-    c->frame_valid = false;  // slot 0's pair buffers are about to be reused
-    c->last_slot = -1;
+    forget_frames(c);  // slot 0's pair buffers are about to be reused
     FrameSlot& f = c->slots[0];
     if (n > f.capacity) {
         CK(cudaDeviceSynchronize());
@@ -997,7 +957,7 @@ int tpdcu_sort_pairs_device(tpdcu_ctx* c, uint64_t* d_keys, uint32_t* d_vals, ui
     CK(launch_sort(so, n, s, nullptr));
     CK(cudaEventRecord(c->sort_ev[1], s));
     CK(launch_sort_copy_result(so, d_keys, d_vals, n, s));
-    CK(cudaMemcpyAsync(&c->status[0].n, f.plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&c->status[TICKET_RING - 1].n, f.plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     c->sort_stream = s;
     c->sort_done = true;
     return TPDCU_OK;
@@ -1011,7 +971,7 @@ int tpdcu_sort_last_ms(tpdcu_ctx* c, float* ms, uint32_t* passes_run) {
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, c->sort_ev[0], c->sort_ev[1]));
     if (ms) *ms = t;
-    if (passes_run) *passes_run = c->status[0].passes_run;
+    if (passes_run) *passes_run = c->status[TICKET_RING - 1].passes_run;
     return TPDCU_OK;
 }
 
