@@ -111,6 +111,12 @@ public:
     void draw(void* hostRgba8, std::size_t pitchBytes) const {
         check(tpdcu_read_frame(_ctx, hostRgba8, pitchBytes), "tpdcu_read_frame");
     }
+    /// draw() without the wait: the copy is enqueued on `stream` (the one passed to rasterFrame) and the caller waits on the
+    /// stream later, so the next rasterFrame can be issued while this frame travels to the host — what the swap-chain
+    /// fences give the reference's render loop (SurfaceRenderer.cpp:254-319).
+    void drawAsync(void* hostRgba8, std::size_t pitchBytes, void* stream) const {
+        check(tpdcu_read_frame_async(_ctx, hostRgba8, pitchBytes, stream), "tpdcu_read_frame_async");
+    }
     /// With a Vulkan swap target bound (bindSwapTarget) draw() only has to wait for CUDA; the Vulkan side then
     /// records copyBufferToImage into the swap image in place of recordTargetCopy.
     void draw() const { check(tpdcu_finish(_ctx, nullptr), "tpdcu_finish"); }

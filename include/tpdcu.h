@@ -72,7 +72,7 @@ int tpdcu_set_transform(tpdcu_ctx* ctx, uint32_t entity, const float m[16]);
 
 int tpdcu_resize(tpdcu_ctx* ctx, uint32_t width, uint32_t height);
 /* Render into caller-owned device memory (R8G8B8A8_UNORM, rows `pitch_bytes` apart, pitch >= 4*width).
- * NULL restores the internal target. */
+ * NULL restores the internal targets (one per frame in flight). */
 int tpdcu_bind_output_device_ptr(tpdcu_ctx* ctx, void* d_rgba8, size_t pitch_bytes);
 /* Render into a Vulkan allocation exported with VK_KHR_external_memory_fd (opaque fd): imported with
  * cudaImportExternalMemory + cudaExternalMemoryGetMappedBuffer; replaces Target + recordTargetCopy's
@@ -99,6 +99,15 @@ int tpdcu_finish(tpdcu_ctx* ctx, uint32_t* pairs);
 /* GaussianEngine::draw's copy (GaussianEngine.cpp:714-762) for callers without Vulkan: copy the
  * finished frame to host memory (rows `host_pitch_bytes` apart). Implies tpdcu_finish. */
 int tpdcu_read_frame(tpdcu_ctx* ctx, void* host_rgba8, size_t host_pitch_bytes);
+
+/* Same copy, enqueued on `stream` (the stream the frame was rastered with) without waiting: the caller synchronises with the
+ * stream or an event of its own. With several frames in flight this lets frame k+1 start while frame k travels to the host —
+ * the role the swap-chain fences play in the reference's loop (SurfaceRenderer.cpp:254-319). P is not looked at here: a frame
+ * that overflowed its buffers is only repeated by the next tpdcu_finish; tpdcu_frames_repeated tells whether any was. */
+int tpdcu_read_frame_async(tpdcu_ctx* ctx, void* host_rgba8, size_t host_pitch_bytes, void* stream);
+/* Checks everything enqueued so far (like tpdcu_finish) and returns how many frames had to be rendered again since
+ * tpdcu_create because they overflowed the grow-only pair buffers or the packed sort word (warm-up frames, in practice). */
+int tpdcu_frames_repeated(tpdcu_ctx* ctx, uint32_t* count);
 
 /* ---- introspection (parity tests, benchmarks); all imply tpdcu_finish -------------------------- */
 
@@ -132,9 +141,9 @@ int tpdcu_set_packed_word_bits(tpdcu_ctx* ctx, uint32_t bits);
  * into a CUDA graph and replayed (the reference re-records two command buffers every frame, GaussianEngine.cpp:637-697).
  * enable: 1/0 to switch replay on/off, -1 to only query. captures/launches (nullable): counters since tpdcu_create. */
 int tpdcu_set_graph_replay(tpdcu_ctx* ctx, int enable, uint32_t* captures, uint32_t* launches);
-/* Frames in flight (1 or 2, default 2), the counterpart of the reference's per-frame Frame objects (GaussianEngine.h:104-117,
- * SurfaceRenderer.h:66): with 2, consecutive tpdcu_raster calls alternate between two sets of per-frame buffers on private
- * streams so that the memory-bound front of frame k+1 overlaps the SM-bound blend of frame k. Ordering seen by the caller
+/* Frames in flight (1..4, default 3), the counterpart of the reference's per-frame Frame objects (GaussianEngine.h:104-117,
+ * SurfaceRenderer.h:66, which keeps 2): consecutive tpdcu_raster calls rotate through that many sets of per-frame buffers on
+ * private streams so that the memory-bound front of the next frames overlaps the SM-bound blend of the current one. Ordering seen by the caller
  * is unchanged: the blend waits for `stream`, `stream` waits for the frame. tpdcu_finish/read_* refer to the newest frame;
  * an older frame that overflowed is re-rendered only if it went to a different target. */
 int tpdcu_set_frames_in_flight(tpdcu_ctx* ctx, int frames);

@@ -358,7 +358,7 @@ def test_two_frames_in_flight_match_serial_rendering(E, oracle):
         serial.append(eng.draw().copy())
     ref = oracle.render(g, ubos[3], w, h, 3)
     assert np.abs(serial[3].astype(np.int32) - ref.rgba.astype(np.int32)).max() <= 1
-    eng.set_frames_in_flight(2)
+    eng.set_frames_in_flight(3)
     # (a) distinct targets, no host sync between frames
     frames = torch.zeros((7, h, w, 4), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream

@@ -32,6 +32,8 @@ TPDCU_SYMBOLS = {
     "tpdcu_raster_views": (i32, [vp, vp, u32, u32, vp, sz, vp]),
     "tpdcu_finish": (i32, [vp, C.POINTER(u32)]),
     "tpdcu_read_frame": (i32, [vp, vp, sz]),
+    "tpdcu_read_frame_async": (i32, [vp, vp, sz, vp]),
+    "tpdcu_frames_repeated": (i32, [vp, C.POINTER(u32)]),
     "tpdcu_get_counts": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
     "tpdcu_read_splats": (i32, [vp, vp, u32]),
     "tpdcu_read_keys": (i32, [vp, vp, u32]),

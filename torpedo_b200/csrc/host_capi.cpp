@@ -102,6 +102,9 @@ int tpdh_engine_raster_frame(tpd::GaussianEngine* e, const tpd::PerspectiveCamer
 int tpdh_engine_draw(tpd::GaussianEngine* e, void* hostRgba8, size_t pitch) {
     return guarded([&] { e->draw(hostRgba8, pitch); });
 }
+int tpdh_engine_draw_async(tpd::GaussianEngine* e, void* hostRgba8, size_t pitch, void* stream) {
+    return guarded([&] { e->drawAsync(hostRgba8, pitch, stream); });
+}
 int tpdh_engine_resize(tpd::GaussianEngine* e, uint32_t w, uint32_t h) {
     return guarded([&] { e->resize(w, h); });
 }

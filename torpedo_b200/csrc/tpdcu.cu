@@ -48,7 +48,7 @@ struct FrameStatus {  // pinned host mirror of what a frame reports back
 };
 static_assert(offsetof(SortPlan, packed_overflow) == 9 * sizeof(uint32_t), "FrameStatus mirrors the head of SortPlan");
 
-constexpr int MAX_SLOTS = 2;
+constexpr int MAX_SLOTS = 4;
 constexpr uint32_t TICKET_RING = 256;  // frames that may be enqueued between two host-side checks (tpdcu_finish & co.)
 
 // What it takes to render a frame again: kept for every frame enqueued since the last check, because P is only looked at
@@ -103,6 +103,8 @@ struct FrameSlot {
     bool graph_valid = false;
     GraphSig graph_sig;
     cudaGraphExec_t graph_exec = nullptr;
+    uint8_t* target = nullptr;  // internal render target of this slot (used when the caller has not bound one)
+    size_t target_bytes = 0;
     bool busy = false;  // something has been enqueued on `stream` since it was last waited for
 };
 
@@ -122,7 +124,7 @@ struct tpdcu_ctx {
     uint64_t models_version = 1;
 
     FrameSlot slots[MAX_SLOTS];
-    int frames_in_flight = 2;
+    int frames_in_flight = 3;
     int next_slot = 0;
 
     uint32_t packed_word_bits = 64;
@@ -134,8 +136,6 @@ struct tpdcu_ctx {
 
     // target
     uint32_t width = 0, height = 0;
-    uint8_t* target = nullptr;  // internal
-    size_t target_bytes = 0;
     uint8_t* bound_out = nullptr;
     size_t bound_pitch = 0;
     cudaExternalMemory_t ext_mem = nullptr;
@@ -145,6 +145,7 @@ struct tpdcu_ctx {
     uint32_t next_status = 0;
     FrameTicket newest{};                // the most recent frame: what finish / read_* / introspection refer to
     bool have_newest = false;
+    uint32_t frames_repeated = 0;        // frames rendered again because they overflowed (grow-only buffers: warm-up only)
 
     bool timing = false;
     cudaEvent_t ev[7] = {};
@@ -262,13 +263,13 @@ static int ensure_status(tpdcu_ctx* c) {
     return TPDCU_OK;
 }
 
-static int ensure_target(tpdcu_ctx* c) {
+static int ensure_target(tpdcu_ctx* c, FrameSlot& f) {
     const size_t need = (size_t)c->width * c->height * 4;
-    if (need <= c->target_bytes && c->target) return TPDCU_OK;
-    cudaFree(c->target);
-    c->target = nullptr;
-    CK(cudaMalloc(&c->target, std::max<size_t>(need, 4)));
-    c->target_bytes = need;
+    if (need <= f.target_bytes && f.target) return TPDCU_OK;
+    cudaFree(f.target);
+    f.target = nullptr;
+    CK(cudaMalloc(&f.target, std::max<size_t>(need, 4)));
+    f.target_bytes = need;
     return TPDCU_OK;
 }
 
@@ -421,12 +422,6 @@ static uint32_t grown_capacity(uint32_t pairs) {
     return (uint32_t)std::min<uint64_t>(want, 0xffffffffull - 2 * SORT_TILE);
 }
 
-static uint8_t* out_ptr(tpdcu_ctx* c, size_t* pitch) {
-    if (c->bound_out) { *pitch = c->bound_pitch; return c->bound_out; }
-    *pitch = (size_t)c->width * 4;
-    return c->target;
-}
-
 static int check_ready(tpdcu_ctx* c) {
     if (!c) return fail(TPDCU_ERR_INVALID, "null context");
     CK(cudaSetDevice(c->device));
@@ -455,6 +450,11 @@ static int raster_one(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cudaSt
     FrameTicket tk{};
     memcpy(tk.ubo, ubo, sizeof(tk.ubo));
     tk.sh_degree = sh_degree;
+    if (!out) {  // no caller-owned target: every frame slot renders into its own internal one
+        if (int r = ensure_target(c, c->slots[slot])) return r;
+        out = c->slots[slot].target;
+        pitch = (size_t)c->width * 4;
+    }
     tk.out = out;
     tk.pitch = pitch;
     tk.user_stream = user;
@@ -495,6 +495,7 @@ static int finish_internal(tpdcu_ctx* c) {
             for (int k = 0; k < MAX_SLOTS; ++k)
                 if (c->slots[k].capacity || k < c->frames_in_flight)
                     if (int r = ensure_pairs(c->slots[k], grown_capacity(max_pairs))) return r;
+        c->frames_repeated += (uint32_t)redo.size();
         for (const FrameTicket& tk : redo) {
             CK(cudaStreamSynchronize(tk.user_stream));
             if (int r = raster_one(c, tk.ubo, tk.sh_degree, tk.user_stream, tk.out, tk.pitch)) return r;
@@ -578,12 +579,11 @@ void tpdcu_destroy(tpdcu_ctx* c) {
     free_scene(c);
     for (auto& f : c->slots) {
         free_slot_pairs(f);
-        cudaFree(f.cam); cudaFree(f.plan); cudaFree(f.zero_region); cudaFree(f.unsorted_keys); cudaFree(f.unsorted_vals);
+        cudaFree(f.cam); cudaFree(f.plan); cudaFree(f.zero_region); cudaFree(f.unsorted_keys); cudaFree(f.unsorted_vals); cudaFree(f.target);
         if (f.stream) cudaStreamDestroy(f.stream);
         if (f.fork) cudaEventDestroy(f.fork);
         if (f.done) cudaEventDestroy(f.done);
     }
-    cudaFree(c->target);
     if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
     if (c->ext_mem) cudaDestroyExternalMemory(c->ext_mem);
     if (c->status) cudaFreeHost(c->status);
@@ -679,7 +679,7 @@ int tpdcu_resize(tpdcu_ctx* c, uint32_t width, uint32_t height) {
     forget_frames(c);
     c->width = width;
     c->height = height;
-    return ensure_target(c);
+    return TPDCU_OK;
 }
 
 int tpdcu_bind_output_device_ptr(tpdcu_ctx* c, void* d_rgba8, size_t pitch_bytes) {
@@ -723,8 +723,7 @@ int tpdcu_raster(tpdcu_ctx* c, const float camera_ubo[TPDCU_CAMERA_FLOATS], uint
     if (!camera_ubo) return fail(TPDCU_ERR_INVALID, "camera_ubo is null");
     if (c->n == 0) return fail(TPDCU_ERR_STATE, "no scene compiled");
     if (c->width == 0) return fail(TPDCU_ERR_STATE, "tpdcu_resize has not been called");
-    size_t pitch; uint8_t* out = out_ptr(c, &pitch);
-    return raster_one(c, camera_ubo, sh_degree, (cudaStream_t)stream, out, pitch);
+    return raster_one(c, camera_ubo, sh_degree, (cudaStream_t)stream, c->bound_out, c->bound_pitch);
 }
 
 int tpdcu_raster_views(tpdcu_ctx* c, const float* camera_ubos, uint32_t n_views, uint32_t sh_degree, void* d_frames,
@@ -765,6 +764,24 @@ int tpdcu_read_frame(tpdcu_ctx* c, void* host_rgba8, size_t host_pitch_bytes) {
     FrameSlot& f = last(c);
     CK(cudaMemcpy2DAsync(host_rgba8, host_pitch_bytes, c->newest.out, c->newest.pitch, (size_t)c->width * 4, c->height, cudaMemcpyDeviceToHost, f.stream));
     CK(cudaStreamSynchronize(f.stream));
+    return TPDCU_OK;
+}
+
+int tpdcu_read_frame_async(tpdcu_ctx* c, void* host_rgba8, size_t host_pitch_bytes, void* stream) {
+    if (int r = check_ready(c)) return r;
+    if (!host_rgba8 || host_pitch_bytes < (size_t)c->width * 4) return fail(TPDCU_ERR_INVALID, "bad host buffer");
+    if (!c->have_newest) return fail(TPDCU_ERR_STATE, "no frame has been rendered");
+    // `stream` must be the stream the frame was rastered with (it already waits for the frame); no host synchronisation here
+    CK(cudaMemcpy2DAsync(host_rgba8, host_pitch_bytes, c->newest.out, c->newest.pitch, (size_t)c->width * 4, c->height,
+                         cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return TPDCU_OK;
+}
+
+int tpdcu_frames_repeated(tpdcu_ctx* c, uint32_t* count) {
+    if (int r = check_ready(c)) return r;
+    if (c->have_newest)
+        if (int r = finish_internal(c)) return r;
+    if (count) *count = c->frames_repeated;
     return TPDCU_OK;
 }
 
@@ -901,7 +918,7 @@ int tpdcu_set_graph_replay(tpdcu_ctx* c, int enable, uint32_t* captures, uint32_
 
 int tpdcu_set_frames_in_flight(tpdcu_ctx* c, int frames) {
     if (int r = check_ready(c)) return r;
-    if (frames < 1 || frames > MAX_SLOTS) return fail(TPDCU_ERR_INVALID, "frames in flight must be 1 or 2");
+    if (frames < 1 || frames > MAX_SLOTS) return fail(TPDCU_ERR_INVALID, "frames in flight must be in [1, 4]");
     if (c->have_newest)
         if (int r = finish_internal(c)) return r;
     if (int r = sync_slots(c)) return r;

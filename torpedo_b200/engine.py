@@ -50,6 +50,7 @@ TPDH_SYMBOLS = {
     "tpdh_engine_transform": (i32, [vp, u32, vp]),
     "tpdh_engine_raster_frame": (i32, [vp, vp, vp]),
     "tpdh_engine_draw": (i32, [vp, vp, sz]),
+    "tpdh_engine_draw_async": (i32, [vp, vp, sz, vp]),
     "tpdh_engine_resize": (i32, [vp, u32, u32]),
     "tpdh_engine_wait_idle": (i32, [vp]),
     "tpdh_engine_handle": (vp, [vp]),
@@ -223,6 +224,15 @@ class GaussianEngine:
             out = np.empty((self.height, self.width, 4), dtype=np.uint8)
         _hcheck(tpdhost().tpdh_engine_draw(self._h, _ptr(out), out.strides[0]))
         return out
+
+    def draw_async(self, out: np.ndarray, stream: int | None = None) -> None:
+        """Enqueue the copy of the newest frame into (pinned) host memory on `stream`; the caller waits on the stream."""
+        _hcheck(tpdhost().tpdh_engine_draw_async(self._h, _ptr(out), out.strides[0], stream))
+
+    def frames_repeated(self) -> int:
+        n = u32(0)
+        check(tpdcu().tpdcu_frames_repeated(self._ctx, C.byref(n)))
+        return n.value
 
     def resize(self, width: int, height: int) -> None:
         _hcheck(tpdhost().tpdh_engine_resize(self._h, width, height))
