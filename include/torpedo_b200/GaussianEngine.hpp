@@ -15,6 +15,7 @@
 #include "../tpdcu.h"
 #include "Camera.hpp"
 #include "GaussianGeometry.hpp"
+#include "PlyLoader.hpp"
 #include "Scene.hpp"
 #include "TransformHost.hpp"
 

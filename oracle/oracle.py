@@ -25,7 +25,8 @@ def build(force: bool = False) -> None:
     """Compile the oracle (and oracle/_ref when /root/reference is present). Building is not using."""
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "tpd_oracle.c")):
         subprocess.run(["make", "-C", _HERE, "libtpd_oracle.so"], check=True, capture_output=True)
-    if os.path.isdir("/root/reference/torpedo") and (force or not os.path.exists(_REF_PATH)):
+    ref_stale = os.path.exists(_REF_PATH) and os.path.getmtime(_REF_PATH) < os.path.getmtime(os.path.join(_HERE, "ref_shim.cpp"))
+    if os.path.isdir("/root/reference/torpedo") and (force or ref_stale or not os.path.exists(_REF_PATH)):
         subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
 
 
@@ -202,6 +203,8 @@ def ref_lib() -> C.CDLL:
         _ref.tpdref_rgb2sh.restype = None
         _ref.tpdref_rgb2sh.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
         _ref.tpdref_sizeof_gaussian_point.restype = C.c_uint32
+        _ref.tpdref_normalize4.restype = None
+        _ref.tpdref_normalize4.argtypes = [C.c_void_p, C.c_void_p]
     return _ref
 
 

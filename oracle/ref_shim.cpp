@@ -47,6 +47,12 @@ void tpdref_rgb2sh(float r, float g, float b, float out48[48]) {
     std::memcpy(out48, sh.data(), sizeof(float) * 48);
 }
 
+// math::normalize(vec4) as used by GaussianPoint::fromModel (volumetric/src/GaussianGeometry.cpp:112-113)
+void tpdref_normalize4(const float in4[4], float out4[4]) {
+    const auto q = tpd::math::normalize(tpd::vec4{ in4[0], in4[1], in4[2], in4[3] });
+    out4[0] = q.x; out4[1] = q.y; out4[2] = q.z; out4[3] = q.w;
+}
+
 uint32_t tpdref_sizeof_gaussian_point() { return sizeof(tpd::GaussianPoint); }
 
 } // extern "C"

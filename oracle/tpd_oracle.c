@@ -489,8 +489,8 @@ void tpdo_from_model_fields(const float* raw59, uint32_t n, float* gaussians) {
         g[0] = r[0]; g[1] = r[1]; g[2] = r[2];
         g[3] = 1.f / (1.f + expf(-r[10]));
         float q[4] = { r[4], r[5], r[6], r[3] }; /* (rot_1, rot_2, rot_3, rot_0) */
-        const float norm = sqrtf(comp_dot4(q, q));
-        for (int k = 0; k < 4; ++k) g[4 + k] = q[k] / norm;
+        const float inv = 1.0f / sqrtf(comp_dot4(q, q)); /* math/vec4.h:226-231: vec / scalar multiplies by the reciprocal */
+        for (int k = 0; k < 4; ++k) g[4 + k] = q[k] * inv;
         g[8] = expf(r[7]); g[9] = expf(r[8]); g[10] = expf(r[9]); g[11] = 1.0f;
         memcpy(g + 12, r + 11, sizeof(float) * 48);
     }

@@ -95,3 +95,53 @@ def test_rgb2sh_and_random_points(E):
     # same recipe as the numpy generator used for the benchmark scenes: bit-identical clouds
     from torpedo_b200 import scenes
     assert (scenes.hello_gaussian(1000, seed=1, with_center=False).view(np.uint32) == pts.view(np.uint32)).all()
+
+
+def _write_ply(path, raw, rest_count, binary=True, extra_first=False):
+    """A 3DGS-style PLY: x y z nx ny nz f_dc_0..2 f_rest_* opacity scale_0..2 rot_0..3 (the order 3DGS trainers write)."""
+    names = ["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"] + [f"f_rest_{k}" for k in range(rest_count)] + \
+            ["opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"]
+    n = raw["x"].shape[0]
+    cols = [raw.get(name, np.zeros(n, np.float32)).astype(np.float32) for name in names]
+    header = "ply\nformat %s 1.0\ncomment test\nelement vertex %d\n" % ("binary_little_endian" if binary else "ascii", n)
+    header += "".join(f"property float {name}\n" for name in names) + "end_header\n"
+    with open(path, "wb") as f:
+        f.write(header.encode())
+        table = np.stack(cols, axis=1)
+        if binary:
+            f.write(table.astype("<f4").tobytes())
+        else:
+            for row in table:
+                f.write((" ".join(repr(float(v)) for v in row) + "\n").encode())
+
+
+@pytest.mark.parametrize("rest_count,binary", [(45, True), (24, True), (0, True), (45, False)])
+def test_from_model_matches_reference_field_transforms(E, oracle, tmp_path, rest_count, binary):
+    """fromModel (GaussianGeometry.cpp:59-127): PLY parsing + sigmoid / quaternion reorder+normalise / exp, bit for bit
+    against the oracle's restatement of :110-117."""
+    rng = np.random.default_rng(rest_count + 1)
+    n = 257
+    raw = {name: rng.normal(size=n).astype(np.float32) for name in
+           ["x", "y", "z", "f_dc_0", "f_dc_1", "f_dc_2", "opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"]}
+    for k in range(rest_count):
+        raw[f"f_rest_{k}"] = rng.normal(size=n).astype(np.float32)
+    path = str(tmp_path / "cloud.ply")
+    _write_ply(path, raw, rest_count, binary)
+    got = E.from_model(path)
+    assert got.shape == (n, 60)
+    raw59 = np.zeros((n, 59), dtype=np.float32)
+    raw59[:, 0:3] = np.stack([raw["x"], raw["y"], raw["z"]], axis=1)
+    raw59[:, 3:7] = np.stack([raw[f"rot_{k}"] for k in range(4)], axis=1)
+    raw59[:, 7:10] = np.stack([raw[f"scale_{k}"] for k in range(3)], axis=1)
+    raw59[:, 10] = raw["opacity"]
+    raw59[:, 11:14] = np.stack([raw[f"f_dc_{k}"] for k in range(3)], axis=1)
+    for k in range(rest_count):
+        raw59[:, 14 + k] = raw[f"f_rest_{k}"]
+    want = np.zeros((n, 60), dtype=np.float32)
+    oracle.lib().tpdo_from_model_fields(raw59.ctypes.data, n, want.ctypes.data)
+    if binary:
+        assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    with pytest.raises(E.TpdError):
+        E.from_model(str(tmp_path / "missing.ply"))

@@ -248,3 +248,9 @@ def test_from_model_field_transforms(oracle):
     np.testing.assert_allclose(out[:, 4:8], q / np.linalg.norm(q, axis=1, keepdims=True), rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(out[:, 8:11], np.exp(raw[:, 7:10].astype(np.float64)), rtol=1e-6)
     assert (out[:, 11] == 1).all() and (out[:, 12:] == raw[:, 11:]).all() and (out[:, :3] == raw[:, :3]).all()
+    if oracle.ref_available():  # the quaternion normalisation is pinned to the reference's own math::normalize(vec4)
+        q_in = np.ascontiguousarray(raw[:, [4, 5, 6, 3]])
+        q_ref = np.zeros_like(q_in)
+        for i in range(len(q_in)):
+            oracle.ref_lib().tpdref_normalize4(q_in[i].ctypes.data, q_ref[i].ctypes.data)
+        assert (q_ref.view(np.uint32) == np.ascontiguousarray(out[:, 4:8]).view(np.uint32)).all()

@@ -3,6 +3,7 @@
 #include "../../include/torpedo_b200/GaussianEngine.hpp"
 
 #include <string>
+#include <vector>
 
 namespace {
 thread_local std::string g_error;
@@ -60,6 +61,19 @@ int tpdh_random_points(uint32_t count, float radius, float minScale, float maxSc
         const auto pts = tpd::GaussianPoint::random(count, radius, { 0.f, 0.f, 0.f }, minScale, maxScale, minOpacity, maxOpacity, seed);
         std::memcpy(out240, pts.data(), pts.size() * sizeof(tpd::GaussianPoint));
     });
+}
+
+// GaussianPoint::fromModel: returns the point count (or -1) and keeps the cloud until tpdh_model_take copies it out
+static thread_local std::vector<tpd::GaussianPoint> g_model;
+int64_t tpdh_model_load(const char* path) {
+    int64_t n = -1;
+    guarded([&] { g_model = tpd::GaussianPoint::fromModel(path); n = static_cast<int64_t>(g_model.size()); });
+    return n;
+}
+void tpdh_model_take(void* out240) {
+    std::memcpy(out240, g_model.data(), g_model.size() * sizeof(tpd::GaussianPoint));
+    g_model.clear();
+    g_model.shrink_to_fit();
 }
 
 // ---- scene ----------------------------------------------------------------------------------------

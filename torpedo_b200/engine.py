@@ -38,6 +38,8 @@ TPDH_SYMBOLS = {
     "tpdh_rgb2sh": (None, [f32, f32, f32, vp]),
     "tpdh_sizeof_gaussian_point": (u32, []),
     "tpdh_random_points": (i32, [u32, f32, f32, f32, f32, f32, C.c_uint64, vp]),
+    "tpdh_model_load": (C.c_int64, [C.c_char_p]),
+    "tpdh_model_take": (None, [vp]),
     "tpdh_scene_create": (vp, []),
     "tpdh_scene_destroy": (None, [vp]),
     "tpdh_scene_add_group": (u32, [vp, vp, u32]),
@@ -91,6 +93,17 @@ def to_cartesian(theta: float, phi: float, radius: float = 1.0) -> np.ndarray:
     """math::to_cartesian (torpedo/math/include/torpedo/math/transform.h:10-16)"""
     out = np.zeros(3, dtype=np.float32)
     tpdhost().tpdh_to_cartesian(theta, phi, radius, _ptr(out))
+    return out
+
+
+def from_model(ply_file: str) -> np.ndarray:
+    """GaussianPoint::fromModel (volumetric/src/GaussianGeometry.cpp:59-127): load a 3DGS point cloud as (n, 60) float32."""
+    n = tpdhost().tpdh_model_load(os.fsencode(ply_file))
+    if n < 0:
+        raise TpdError(tpdhost().tpdh_last_error().decode())
+    out = np.zeros((n, 60), dtype=np.float32)
+    if n:
+        tpdhost().tpdh_model_take(_ptr(out))
     return out
 
 
