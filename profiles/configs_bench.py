@@ -41,8 +41,20 @@ def run(name, g, w, h, deg, cam, model=None, reps=20):
         runs.append(eng.stage_times_ms())
     eng.enable_stage_timing(False)
     st = {k: round(statistics.median(r[k] for r in runs), 4) for k in runs[0]}
+    # throughput with frames in flight: K back-to-back frames, one host sync at the end
+    import torch
+    for _ in range(4):
+        eng.raster_frame(cam)
+    eng.finish()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(40):
+        eng.raster_frame(cam)
+    eng.finish()
+    torch.cuda.synchronize()
+    throughput_ms = (time.perf_counter() - t0) * 1e3 / 40
     pairs, visible = eng.counts()
-    res = {"config": name, "n": int(g.shape[0]), "w": w, "h": h, "sh": deg, "pairs": pairs, "visible": visible, "stages_ms": st,
+    res = {"config": name, "n": int(g.shape[0]), "w": w, "h": h, "sh": deg, "pairs": pairs, "visible": visible, "ms_per_frame_3_in_flight": round(throughput_ms, 4), "stages_ms": st,
            "sort": eng.sort_info(), "sort_gkeys_per_s": round(pairs / ((st["sort_hist"] + st["sort_passes"]) * 1e6), 2) if pairs else None}
     if not skip_parity:
         img = eng.draw()
