@@ -196,34 +196,22 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
             const float cy = q1.x * dy * dy;
             const float p0 = fmaf(dx0, fmaf(q0.z, dx0, by), cy);   // A'dx^2 + B'dx dy + C'dy^2 = log2(e) * power
             const float p1 = fmaf(dx1, fmaf(q0.z, dx1, by), cy);
-            if (fmaxf(p0, p1) < q1.z) continue;                     // alpha < 1/255 at both pixels (blend.slang:89)
+            // Straight-line, predicated update of both pixels: only ~1/3 of the lanes get here for a typical splat, so
+            // branch (re)convergence would cost more than the arithmetic it skips.
+            const bool h0 = (live & 1u) && p0 <= 0.0f && p0 >= q1.z;    // power > 0 is skipped (blend.slang:85); below the
+            const bool h1 = (live & 2u) && p1 <= 0.0f && p1 >= q1.z;    // threshold alpha < 1/255 (blend.slang:89)
+            if (!(h0 || h1)) continue;
             const float4 c = sm.col[e];
-            if ((live & 1u) && p0 <= 0.0f) {                        // power > 0 is skipped (blend.slang:85)
-                const float alpha = fminf(0.99f, q1.y * ex2_approx(p0));
-                if (alpha >= 1.0f / 255.0f) {
-                    const float test_T = T0 * (1.0f - alpha);
-                    if (test_T < 0.0001f) {
-                        live &= ~1u;                                // done; this splat is NOT added (blend.slang:92-95)
-                    } else {
-                        const float w = alpha * T0;
-                        r0 = fmaf(c.x, w, r0); g0 = fmaf(c.y, w, g0); b0 = fmaf(c.z, w, b0);
-                        T0 = test_T;
-                    }
-                }
-            }
-            if ((live & 2u) && p1 <= 0.0f) {
-                const float alpha = fminf(0.99f, q1.y * ex2_approx(p1));
-                if (alpha >= 1.0f / 255.0f) {
-                    const float test_T = T1 * (1.0f - alpha);
-                    if (test_T < 0.0001f) {
-                        live &= ~2u;
-                    } else {
-                        const float w = alpha * T1;
-                        r1 = fmaf(c.x, w, r1); g1 = fmaf(c.y, w, g1); b1 = fmaf(c.z, w, b1);
-                        T1 = test_T;
-                    }
-                }
-            }
+            const float a0 = fminf(0.99f, q1.y * ex2_approx(p0)), a1 = fminf(0.99f, q1.y * ex2_approx(p1));
+            const float t0 = T0 * (1.0f - a0), t1 = T1 * (1.0f - a1);
+            const bool v0 = h0 && a0 >= 1.0f / 255.0f, v1 = h1 && a1 >= 1.0f / 255.0f;
+            const bool k0 = v0 && t0 < 0.0001f, k1 = v1 && t1 < 0.0001f;  // done; this splat is NOT added (blend.slang:92-95)
+            live &= ~((k0 ? 1u : 0u) | (k1 ? 2u : 0u));
+            const float w0 = (v0 && !k0) ? a0 * T0 : 0.0f, w1 = (v1 && !k1) ? a1 * T1 : 0.0f;
+            r0 = fmaf(c.x, w0, r0); g0 = fmaf(c.y, w0, g0); b0 = fmaf(c.z, w0, b0);
+            r1 = fmaf(c.x, w1, r1); g1 = fmaf(c.y, w1, g1); b1 = fmaf(c.z, w1, b1);
+            T0 = (v0 && !k0) ? t0 : T0;
+            T1 = (v1 && !k1) ? t1 : T1;
         }
         // block vote (blend.slang:56-63); also the barrier that lets the queue be refilled
         const bool finished = in >= range.y;
