@@ -85,17 +85,34 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 struct BlendEntry {
-    float4 g0;  // px, py, A', B'
-    float4 g1;  // C', opacity, power2 threshold, -
+    float4 g0;   // px, py, A', B'
+    float4 g1;   // C', opacity, power2 threshold, -
+    float4 col;  // r, g, b, -
 };
+static_assert(sizeof(BlendEntry) * BLEND_QUEUE <= 65536, "the per-quadrant lists hold 16-bit byte offsets into ent[]");
 struct BlendSmem {
     BlendEntry ent[BLEND_QUEUE];
-    float4 col[BLEND_QUEUE];                     // r, g, b
-    uint16_t list[BLEND_WARPS][BLEND_QUEUE];     // per-quadrant queue entry indices, in sorted order
+    uint16_t list[BLEND_WARPS][BLEND_QUEUE];     // per-quadrant byte offsets of queue entries, in sorted order
     uint32_t cnt[BLEND_WARPS][BLEND_WARPS + 1];  // [staging warp][tile, quadrant 0..3] survivors of the current round
 };
 
-__global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a) {
+// Shared-memory loads by 32-bit shared-window address: the drain loop below is instruction-bound, and these keep the
+// address arithmetic down to one add per splat.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+
+#ifndef TPDCU_BLEND_MINB
+#define TPDCU_BLEND_MINB 7
+#endif
+__global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(RasterLaunch a) {
     __shared__ BlendSmem sm;
 
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX;
@@ -116,12 +133,17 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
     const uint2 range = reinterpret_cast<const uint2*>(a.ranges)[tile];
     const float4* __restrict__ geo4 = reinterpret_cast<const float4*>(a.geo);
 
-    uint32_t live = 0;  // bit k: pixel (x0 + k, y0) is still accumulating
+    uint32_t inside = 0;  // bit k: pixel (x0 + k, y0) is inside the image
     if (y0 < a.height) {
-        if (x0 < a.width) live |= 1u;
-        if (x0 + 1u < a.width) live |= 2u;
+        if (x0 < a.width) inside |= 1u;
+        if (x0 + 1u < a.width) inside |= 2u;
     }
-    const uint32_t inside = live;
+    // Upper bound of the accepted power per pixel: 0 while the pixel is accumulating (power > 0 is skipped,
+    // blend.slang:85), -inf once it is done or if it lies outside the image, so that one compare covers both tests.
+    const float NEG_INF = __int_as_float(0xff800000);
+    float u0 = (inside & 1u) ? 0.0f : NEG_INF, u1 = (inside & 2u) ? 0.0f : NEG_INF;
+    const uint32_t ent_s = (uint32_t)__cvta_generic_to_shared(&sm.ent[0]);
+    const uint32_t list_s = (uint32_t)__cvta_generic_to_shared(&sm.list[warp][0]);
     float T0 = 1.0f, T1 = 1.0f, r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
 
     uint32_t in = range.x;
@@ -170,10 +192,10 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
                 const float4 col = __ldg(a.color + g);
                 sm.ent[pos].g0 = make_float4(ra.x, ra.y, (-0.5f * LOG2E) * ra.z, -LOG2E * ra.w);
                 sm.ent[pos].g1 = make_float4((-0.5f * LOG2E) * rb.x, rb.y, -__log2f(255.0f * rb.y) - 0.01f, 0.0f);
-                sm.col[pos] = col;
+                sm.ent[pos].col = col;
 #pragma unroll
                 for (uint32_t q = 0; q < BLEND_WARPS; ++q)
-                    if (keep & (2u << q)) sm.list[q][ln[q] + before[q + 1] + __popc(ballot[q + 1] & lanemask_lt())] = (uint16_t)pos;
+                    if (keep & (2u << q)) sm.list[q][ln[q] + before[q + 1] + __popc(ballot[q + 1] & lanemask_lt())] = (uint16_t)(pos * sizeof(BlendEntry));
             }
             qn += total[0];
 #pragma unroll
@@ -184,12 +206,13 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
 
         // ---- drain: front-to-back compositing (blend.slang:77-100) over this quadrant's list --------------------------
         const uint32_t my_ln = warp == 0 ? ln[0] : warp == 1 ? ln[1] : warp == 2 ? ln[2] : ln[3];
-        const uint16_t* my_list = sm.list[warp];
+#pragma unroll 2
         for (uint32_t j = 0; j < my_ln; ++j) {
-            if ((j & 7u) == 0u && __all_sync(0xffffffffu, live == 0)) break;  // the whole quadrant is done (uniform branch)
-            const uint32_t e = my_list[j];
-            const float4 q0 = sm.ent[e].g0;
-            const float4 q1 = sm.ent[e].g1;
+            // the whole quadrant is done (uniform branch)
+            if ((j & 7u) == 0u && __all_sync(0xffffffffu, u0 < 0.0f && u1 < 0.0f)) break;
+            const uint32_t e = ent_s + lds_u16(list_s + 2u * j);
+            const float4 q0 = lds_f4(e);
+            const float4 q1 = lds_f4(e + 16u);
             const float dx0 = q0.x - fx0, dy = q0.y - fy0;
             const float dx1 = dx0 - 1.0f;
             const float by = q0.w * dy;
@@ -198,24 +221,26 @@ __global__ void __launch_bounds__(BLEND_THREADS, 8) blend_kernel(RasterLaunch a)
             const float p1 = fmaf(dx1, fmaf(q0.z, dx1, by), cy);
             // Straight-line, predicated update of both pixels: only ~1/3 of the lanes get here for a typical splat, so
             // branch (re)convergence would cost more than the arithmetic it skips.
-            const bool h0 = (live & 1u) && p0 <= 0.0f && p0 >= q1.z;    // power > 0 is skipped (blend.slang:85); below the
-            const bool h1 = (live & 2u) && p1 <= 0.0f && p1 >= q1.z;    // threshold alpha < 1/255 (blend.slang:89)
+            const bool h0 = p0 <= u0 && p0 >= q1.z;    // below the threshold alpha < 1/255 (blend.slang:89)
+            const bool h1 = p1 <= u1 && p1 >= q1.z;
             if (!(h0 || h1)) continue;
-            const float4 c = sm.col[e];
+            const float4 c = lds_f4(e + 32u);
             const float a0 = fminf(0.99f, q1.y * ex2_approx(p0)), a1 = fminf(0.99f, q1.y * ex2_approx(p1));
-            const float t0 = T0 * (1.0f - a0), t1 = T1 * (1.0f - a1);
+            const float w0 = a0 * T0, w1 = a1 * T1;
+            const float t0 = T0 - w0, t1 = T1 - w1;    // T (1 - alpha)
             const bool v0 = h0 && a0 >= 1.0f / 255.0f, v1 = h1 && a1 >= 1.0f / 255.0f;
-            const bool k0 = v0 && t0 < 0.0001f, k1 = v1 && t1 < 0.0001f;  // done; this splat is NOT added (blend.slang:92-95)
-            live &= ~((k0 ? 1u : 0u) | (k1 ? 2u : 0u));
-            const float w0 = (v0 && !k0) ? a0 * T0 : 0.0f, w1 = (v1 && !k1) ? a1 * T1 : 0.0f;
-            r0 = fmaf(c.x, w0, r0); g0 = fmaf(c.y, w0, g0); b0 = fmaf(c.z, w0, b0);
-            r1 = fmaf(c.x, w1, r1); g1 = fmaf(c.y, w1, g1); b1 = fmaf(c.z, w1, b1);
-            T0 = (v0 && !k0) ? t0 : T0;
-            T1 = (v1 && !k1) ? t1 : T1;
+            const bool s0 = v0 && t0 >= 0.0001f, s1 = v1 && t1 >= 0.0001f;  // the splat is added (blend.slang:92-98) ...
+            u0 = (v0 && !s0) ? NEG_INF : u0;                                // ... else the pixel is done and it is NOT
+            u1 = (v1 && !s1) ? NEG_INF : u1;
+            const float m0 = s0 ? w0 : 0.0f, m1 = s1 ? w1 : 0.0f;
+            r0 = fmaf(c.x, m0, r0); g0 = fmaf(c.y, m0, g0); b0 = fmaf(c.z, m0, b0);
+            r1 = fmaf(c.x, m1, r1); g1 = fmaf(c.y, m1, g1); b1 = fmaf(c.z, m1, b1);
+            T0 = s0 ? t0 : T0;
+            T1 = s1 ? t1 : T1;
         }
         // block vote (blend.slang:56-63); also the barrier that lets the queue be refilled
         const bool finished = in >= range.y;
-        if (__syncthreads_and(live == 0) || finished) break;
+        if (__syncthreads_and(u0 < 0.0f && u1 < 0.0f) || finished) break;
     }
 
     if (inside & 1u)
