@@ -142,8 +142,13 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
     // blend.slang:85), -inf once it is done or if it lies outside the image, so that one compare covers both tests.
     const float NEG_INF = __int_as_float(0xff800000);
     float u0 = (inside & 1u) ? 0.0f : NEG_INF, u1 = (inside & 2u) ? 0.0f : NEG_INF;
-    const uint32_t ent_s = (uint32_t)__cvta_generic_to_shared(&sm.ent[0]);
+    uint32_t ent_s = (uint32_t)__cvta_generic_to_shared(&sm.ent[0]);
     const uint32_t list_s = (uint32_t)__cvta_generic_to_shared(&sm.list[warp][0]);
+    // ptxas would otherwise re-derive these three loop invariants inside the drain loop (5 instructions per 2 splats)
+    // to save registers; a value that went through a shuffle cannot be rematerialised.
+    ent_s = __shfl_sync(0xffffffffu, ent_s, lane);
+    fx0 = __shfl_sync(0xffffffffu, fx0, lane);
+    fy0 = __shfl_sync(0xffffffffu, fy0, lane);
     float T0 = 1.0f, T1 = 1.0f, r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
 
     uint32_t in = range.x;
