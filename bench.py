@@ -332,14 +332,13 @@ def run_gpu(args):
         total_frames = K * world
         ms_per_frame = elapsed_ms / total_frames
         peak, peak_src = measured_peak_hbm()
-        passes = max(int(stages["passes_run"]), 1)
-        pass_ms = stages["sort_passes"] / passes
-        if sort_info["packed"]:   # single 64-bit words: 8 B in + 8 B out per pass; the first pass reads (key, value) pairs: 12 B in
-            alg_bytes = stage_pairs * (20.0 + 16.0 * (passes - 1)) / passes
-        else:                     # (u64 key, u32 value) pairs: 12 B in + 12 B out per pass
-            alg_bytes = stage_pairs * 24.0
+        # dominant HBM-bound kernel of the sort: one onesweep pass over the pair words (8 B in + 8 B out per pair)
+        passes = max(int(stages["tile_passes_run"]), 1)
+        pass_ms = (stages["tile_sort"] - stages["tile_sort_hist_plan"]) / passes
+        alg_bytes = stage_pairs * 16.0
         achieved = alg_bytes / (pass_ms * 1e-3) / 1e9 if pass_ms > 0 else 0.0
-        sort_ms = stages["sort_hist"] + stages["sort_passes"]
+        sort_ms = stages["depth_sort"] + stages["tile_sort"]
+        depth_passes = int(stages["depth_passes_run"])
         line = {
             "metric": METRIC, "value": ms_per_frame, "unit": "ms/frame", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -353,8 +352,9 @@ def run_gpu(args):
             "frames_in_flight": 3, "single_frame_latency_ms": stages["frame"],
             "stages_ms": stages,
             "sort_gkeys_per_s": stage_pairs / (sort_ms * 1e-3) / 1e9 if sort_ms > 0 else None,
-            "sort": dict(sort_info, passes_run=passes, bytes_per_pair=(8 + 20 + 16 * (passes - 1)) if sort_info["packed"] else (8 + 24 * passes)),
-            "roofline": {"kernel": "onesweep_kernel (one 8-bit digit pass of the tile|depth|index sort; average over the passes of a frame)", "bound": "hbm",
+            "sort": dict(sort_info, design="two-level: visible Gaussians by depth, duplication in depth order, pairs by tile",
+                         bytes_per_pair=8 + 16 * passes, bytes_per_visible_gaussian=8 + 16 * depth_passes),
+            "roofline": {"kernel": "onesweep_kernel<WORDS> (one 8-bit digit pass of the tile sort over the pair words; average over the passes of a frame)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": ncu_traffic_per_launch(), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pass_ms,
                          "peak_source": peak_src},
@@ -362,9 +362,10 @@ def run_gpu(args):
                     "steps": e2e_steps, "checksum": checksum, "serial_latency_ms": e2e_serial_ms / e2e_steps,
                     "frames_repeated": repeats,
                     "note": "lookAt on host -> rasterFrame -> drawAsync into pinned host memory, frames in flight as in the reference's loop"},
-            # per frame: setup, preprocess (geometry+scan+duplication), colour, histogram, plan, ranges, blend + one onesweep
-            # launch per 8-bit digit of the widest possible key (a pass whose digit is constant still launches and exits)
-            "gpu_launches": K * (7 + (32 + ((WIDTH + 15) // 16 * ((HEIGHT + 15) // 16) - 1).bit_length() + 7) // 8),
+            # per frame: setup, preprocess, colour, duplication, ranges, blend, 2 x (histogram, plan) + one onesweep launch per
+            # 8-bit digit of the widest possible key of each sort: 4 for the 32 depth bits (a pass whose digit is constant
+            # still launches and exits), ceil(tile_bits / 8) for the tiles
+            "gpu_launches": K * (10 + 4 + ((((WIDTH + 15) // 16 * ((HEIGHT + 15) // 16) - 1).bit_length() + 7) // 8)),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -35,7 +35,7 @@ extern "C" {
 #define TPDCU_SPLAT_BYTES 48     /* splat.slang:33-39, GaussianEngine.h:124 */
 #define TPDCU_CAMERA_FLOATS 34   /* splat.slang:18-22: view(16) | proj*view(16) | focalNDC(2) */
 #define TPDCU_TILE 16            /* BLOCK_X == BLOCK_Y, GaussianEngine.h:122-123 */
-#define TPDCU_NUM_STAGES 8
+#define TPDCU_NUM_STAGES 11
 
 typedef struct tpdcu_ctx tpdcu_ctx;
 
@@ -106,7 +106,7 @@ int tpdcu_read_frame(tpdcu_ctx* ctx, void* host_rgba8, size_t host_pitch_bytes);
  * that overflowed its buffers is only repeated by the next tpdcu_finish; tpdcu_frames_repeated tells whether any was. */
 int tpdcu_read_frame_async(tpdcu_ctx* ctx, void* host_rgba8, size_t host_pitch_bytes, void* stream);
 /* Checks everything enqueued so far (like tpdcu_finish) and returns how many frames had to be rendered again since
- * tpdcu_create because they overflowed the grow-only pair buffers or the packed sort word (warm-up frames, in practice). */
+ * tpdcu_create because they overflowed the grow-only pair buffers (warm-up frames, in practice). */
 int tpdcu_frames_repeated(tpdcu_ctx* ctx, uint32_t* count);
 
 /* ---- introspection (parity tests, benchmarks); all imply tpdcu_finish -------------------------- */
@@ -121,22 +121,20 @@ int tpdcu_read_splats(tpdcu_ctx* ctx, void* host_splats48, uint32_t n);
 int tpdcu_read_keys(tpdcu_ctx* ctx, uint64_t* host_keys, uint32_t count);
 int tpdcu_read_values(tpdcu_ctx* ctx, uint32_t* host_vals, uint32_t count);
 int tpdcu_read_ranges(tpdcu_ctx* ctx, uint32_t* host_ranges2, uint32_t tile_count);
-/* When enabled, every frame also keeps a copy of the UNSORTED pairs as emitted by the duplication
- * stage (keygen.slang order); costs one extra device copy per frame. Off by default. */
-int tpdcu_keep_unsorted(tpdcu_ctx* ctx, int enable);
+/* The reference's UNSORTED key/value buffers (keygen.slang:47-53: Gaussian i writes its tiles row-major at its prefix
+ * offset). The frame never materialises them — its duplication stage runs over the depth-sorted Gaussians — so this
+ * call rebuilds them from the last frame's per-Gaussian records, in the reference's order. */
 int tpdcu_read_unsorted(tpdcu_ctx* ctx, uint64_t* host_keys, uint32_t* host_vals, uint32_t count);
 /* When enabled, CUDA events bracket every stage of each frame. times_ms (last finished frame):
- * [0] camera+setup [1] preprocess+scan+duplicate [2] sort histogram+plan [3] sort passes
- * [4] ranges [5] blend [6] whole frame [7] number of onesweep passes that actually ran. */
+ * [0] clear+camera setup [1] preprocess (projection, scan, visible compaction) + SH colour [2] depth sort of the visible
+ * Gaussians [3] duplication [4] tile sort of the pairs [5] ranges [6] blend [7] whole frame
+ * [8] / [9] number of onesweep passes the depth sort / the tile sort actually ran [10] histogram+plan share of [4]. */
 int tpdcu_enable_stage_timing(tpdcu_ctx* ctx, int enable);
 int tpdcu_stage_times_ms(tpdcu_ctx* ctx, float times_ms[TPDCU_NUM_STAGES]);
-/* How the last finished frame was sorted. packed = 1: single 64-bit words  tile | depth - bias | index  (16 B moved per
- * pair and pass; the first pass reads pairs: 20 B), packed = 0: (u64 key, u32 value) pairs (24 B per pair and pass).
- * depth_bits / idx_bits / total_bits: widths of the depth-minus-bias field, the index field and the sorted bit range. */
-int tpdcu_get_sort_info(tpdcu_ctx* ctx, uint32_t* packed, uint32_t* depth_bits, uint32_t* idx_bits, uint32_t* total_bits);
-/* Testing aid: pretend packed sort words are only `bits` wide (default 64). A frame whose tile|depth|index does not fit is
- * detected on the device and re-rendered in pair mode; this knob lets the tests exercise that path on small scenes. */
-int tpdcu_set_packed_word_bits(tpdcu_ctx* ctx, uint32_t bits);
+/* How the last finished frame was sorted (two levels, see csrc/sort.cu): the visible Gaussians by the `depth_bits` bits the
+ * frame's depth range occupies (words depth << 32 | index, 16 B moved per Gaussian and pass), then the pairs by their
+ * `tile_bits` tile bits (words tile << 32 | index, 16 B per pair and pass); *_passes = onesweep passes that ran. */
+int tpdcu_get_sort_info(tpdcu_ctx* ctx, uint32_t* depth_bits, uint32_t* depth_passes, uint32_t* tile_bits, uint32_t* tile_passes);
 /* The frame's launches between the camera setup and the blend do not change from frame to frame; they are captured once
  * into a CUDA graph and replayed (the reference re-records two command buffers every frame, GaussianEngine.cpp:637-697).
  * enable: 1/0 to switch replay on/off, -1 to only query. captures/launches (nullable): counters since tpdcu_create. */

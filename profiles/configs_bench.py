@@ -55,7 +55,7 @@ def run(name, g, w, h, deg, cam, model=None, reps=20):
     throughput_ms = (time.perf_counter() - t0) * 1e3 / 40
     pairs, visible = eng.counts()
     res = {"config": name, "n": int(g.shape[0]), "w": w, "h": h, "sh": deg, "pairs": pairs, "visible": visible, "ms_per_frame_3_in_flight": round(throughput_ms, 4), "stages_ms": st,
-           "sort": eng.sort_info(), "sort_gkeys_per_s": round(pairs / ((st["sort_hist"] + st["sort_passes"]) * 1e6), 2) if pairs else None}
+           "sort": eng.sort_info(), "sort_gkeys_per_s": round(pairs / ((st["depth_sort"] + st["tile_sort"]) * 1e6), 2) if pairs else None}
     if not skip_parity:
         img = eng.draw()
         keys, vals = eng.read_sorted()

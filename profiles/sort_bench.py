@@ -24,14 +24,12 @@ eng = E.GaussianEngine(w, h)
 eng.compile(scene, E.Settings(3))
 cam = E.PerspectiveCamera(w, h)
 cam.look_at(E.to_cartesian(*bench.ring_camera_params(0)), (0, 0, 0), (0, 0, 1))
-eng.keep_unsorted(True)
 eng.raster_frame(cam)
 eng.finish()
 eng.raster_frame(cam)
 pairs = eng.finish()
 uk, uv = eng.read_unsorted()
 sk, sv = eng.read_sorted()
-eng.keep_unsorted(False)
 keys0 = torch.from_numpy(uk.view(np.int64)).cuda()
 vals0 = torch.from_numpy(uv.view(np.int32)).cuda()
 order = torch.sort(keys0, stable=True).indices

@@ -12,7 +12,7 @@ TPDHOST_PATH = os.path.join(LIB_DIR, "libtpdhost.so")
 CAMERA_FLOATS = 34
 GAUSSIAN_BYTES = 240
 SPLAT_BYTES = 48
-NUM_STAGES = 8
+NUM_STAGES = 11
 
 u32, vp, sz, i32 = C.c_uint32, C.c_void_p, C.c_size_t, C.c_int
 
@@ -39,12 +39,10 @@ TPDCU_SYMBOLS = {
     "tpdcu_read_keys": (i32, [vp, vp, u32]),
     "tpdcu_read_values": (i32, [vp, vp, u32]),
     "tpdcu_read_ranges": (i32, [vp, vp, u32]),
-    "tpdcu_keep_unsorted": (i32, [vp, i32]),
     "tpdcu_read_unsorted": (i32, [vp, vp, vp, u32]),
     "tpdcu_enable_stage_timing": (i32, [vp, i32]),
     "tpdcu_stage_times_ms": (i32, [vp, vp]),
     "tpdcu_get_sort_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
-    "tpdcu_set_packed_word_bits": (i32, [vp, u32]),
     "tpdcu_set_graph_replay": (i32, [vp, i32, C.POINTER(u32), C.POINTER(u32)]),
     "tpdcu_set_frames_in_flight": (i32, [vp, i32]),
     "tpdcu_get_capacity": (i32, [vp, C.POINTER(u32)]),

@@ -25,30 +25,40 @@ constexpr uint32_t SORT_KPT = TPDCU_SORT_KPT;  // keys per thread
 constexpr uint32_t SORT_TILE = SORT_THREADS * SORT_KPT;
 constexpr uint32_t SORT_WARPS = SORT_THREADS / 32;
 
+// Tickets and digit histograms of one radix sort.
+struct SortCtl {
+    uint32_t ticket[SORT_MAX_PASSES];
+    uint32_t hist[SORT_MAX_PASSES][SORT_BINS];  // global digit histograms (then exclusive offsets)
+};
+
 // Per-frame control block; lives at the head of the per-frame zeroed region.
 struct FrameCtl {
     uint32_t scan_ticket;                 // preprocess partition tickets
+    uint32_t emit_ticket;                 // duplication partition tickets
     uint32_t pairs_total;                 // P (tilesRendered), may exceed capacity
     uint32_t visible;                     // Gaussians with tiles > 0
     uint32_t depth_max;                   // max float bits of viewZ over the visible Gaussians (atomicMax)
     uint32_t inv_depth_min;               // ~min float bits (atomicMax on the complement, so zero-init works)
-    uint32_t pad0[3];
-    uint32_t sort_ticket[SORT_MAX_PASSES];
-    uint32_t hist[SORT_MAX_PASSES][SORT_BINS];  // global digit histograms (then exclusive offsets)
+    uint32_t pad0[2];
+    SortCtl depth_sort;                   // visible Gaussians by view depth
+    SortCtl tile_sort;                    // (tile, Gaussian) pairs by tile; also the standalone pair sort
 };
 
-// Written by the plan kernel, read by every sort pass and by the consumers of the sorted pairs.
+// Which sort a launch performs: where n and the key geometry come from.
+//   SORT_KIND_PAIRS  standalone API: (u64 key, u32 value) pairs, bits [0, end_bit), n from the host
+//   SORT_KIND_DEPTH  words  float_bits(viewZ) << 32 | Gaussian index, n = FrameCtl::visible, sorted on (depth - frame
+//                    minimum): only the bits the frame's depth range occupies are sorted (26 at 1080p with default planes)
+//   SORT_KIND_TILE   words  tile << 32 | Gaussian index, n = min(FrameCtl::pairs_total, capacity), end_bit tile bits
+enum : uint32_t { SORT_KIND_PAIRS = 0, SORT_KIND_DEPTH = 1, SORT_KIND_TILE = 2 };
+
+// Written by the plan kernel, read by every sort pass and by the consumers of the sorted result.
 struct SortPlan {
-    uint32_t n;                           // number of pairs to sort (min(P, capacity))
+    uint32_t n;                           // number of elements to sort
     uint32_t num_passes;
     uint32_t final_sel;                   // which ping-pong buffer holds the result
     uint32_t passes_run;
-    uint32_t bias;                        // subtracted from the low (depth) word of every key before digit extraction
-    uint32_t depth_bits;                  // significant bits of (depth - bias); the tile id is packed right above them
-    uint32_t total_bits;                  // depth_bits + tile bits: what the passes actually sort on
-    uint32_t idx_bits;                    // packed mode: low bits of every word that hold the Gaussian index (else 0)
-    uint32_t packed;                      // 1: the sorted result is ONE array of packed words (see sort.cu), 0: key/value pairs
-    uint32_t packed_overflow;             // 1: this frame's tile|depth|index does not fit 64 bits -> results invalid, re-render in pair mode
+    uint32_t bias;                        // words: subtracted from the key (high 32 bits) before digit extraction
+    uint32_t total_bits;                  // key bits the passes sort on
     uint32_t pad[2];
     uint32_t skip[SORT_MAX_PASSES];       // pass is an identity permutation (single occupied bin)
     uint32_t src_sel[SORT_MAX_PASSES];    // ping-pong buffer the pass reads from
@@ -74,7 +84,8 @@ static_assert(sizeof(SplatGeo) == 32, "SplatGeo must be one 32-byte sector");
 struct SplatArrays {
     SplatGeo* geo;                        // written for visible Gaussians only
     float4* color;                        // rgb (+pad), written for visible Gaussians only
-    float2* depth_radius;                 // (viewZ, radius), visible only; read by tpdcu_read_splats
+    float2* depth_radius;                 // (viewZ, radius), visible only; read by the introspection exports
+    uint2* rect;                          // tile rectangle (x0 | y0 << 16, w | h << 16), visible only
     uint32_t* offsets;                    // exclusive pair offset per Gaussian, n + 1 entries (prefix.slang semantics)
 };
 
@@ -128,14 +139,12 @@ struct PreprocessLaunch {
     FrameCtl* ctl;
     uint64_t* scan_desc;                  // zeroed, one per partition
     SplatArrays out;
-    uint64_t* keys;
-    uint32_t* vals;
-    uint32_t capacity;
+    uint64_t* depth_words;                // out: float_bits(viewZ) << 32 | index of every visible Gaussian, index order
     uint32_t width, height, sh_degree;
 };
 struct CameraUbo { float f[34]; };          // the reference's 136-byte Camera block, passed by value
 cudaError_t launch_setup(const PreprocessLaunch& a, const CameraUbo& ubo, cudaStream_t s);
-cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s);   // geometry + scan + duplication
+cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s);   // geometry + scan + visible compaction
 cudaError_t launch_color(const PreprocessLaunch& a, cudaStream_t s);        // SH colour of the visible Gaussians
 
 struct CompileLaunch {
@@ -148,40 +157,59 @@ struct CompileLaunch {
 };
 cudaError_t launch_compile_scene(const CompileLaunch& a, cudaStream_t s);
 
-struct SortLaunch {
-    uint64_t* keys[2];
-    uint32_t* vals[2];
+// Duplication (keygen.slang) over the depth-sorted visible Gaussians: pairs come out ordered by (depth, index), so that the
+// stable sort by tile that follows yields the reference's (tile, depth) order.
+struct EmitLaunch {
+    const uint64_t* depth_words[2];       // ping-pong buffers of the depth sort
+    const SortPlan* depth_plan;           // which of them holds the result, and how many Gaussians are visible
+    const uint2* rect;
     FrameCtl* ctl;
+    uint64_t* scan_desc;                  // zeroed, one per partition
+    uint64_t* keys;                       // out: tile << 32 | index
+    uint32_t n;                           // scene size (launch bound)
+    uint32_t capacity;
+    uint32_t width;
+};
+cudaError_t launch_emit(const EmitLaunch& a, cudaStream_t s);
+
+// introspection: the reference's unsorted (key, value) buffers, in the reference's (index) order
+cudaError_t launch_export_unsorted(const SplatArrays& a, uint32_t n, uint32_t width, uint64_t* keys, uint32_t* vals, uint32_t capacity,
+                                   cudaStream_t s);
+
+struct SortLaunch {
+    uint64_t* keys[2];                    // pair keys, or words
+    uint32_t* vals[2];                    // SORT_KIND_PAIRS only
+    FrameCtl* frame;                      // n and depth range (SORT_KIND_DEPTH / SORT_KIND_TILE)
+    SortCtl* ctl;
     SortPlan* plan;
     uint32_t* lookback;                   // zeroed, [num_passes][parts_cap][SORT_BINS]
+    uint32_t kind;
     uint32_t capacity;                    // launch bound for grids
-    uint32_t end_bit;                     // 32 + tile bits (frame path) or the caller's end bit (standalone)
-    uint32_t packed_idx_bits;             // 0: pair mode; else bits reserved for the Gaussian index in packed words
-    uint32_t packed_word_bits;            // 64 (testing aid: smaller values force the overflow -> pair-mode fallback)
+    uint32_t end_bit;                     // pairs: end bit of the key; depth: 32; tile: tile bits
     int sm_count;
 };
-// n is taken from ctl->pairs_total clamped to capacity (frame path) when n_host == UINT32_MAX,
-// else from n_host (standalone sort).
+// n_host is used by SORT_KIND_PAIRS only.
 cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cudaEvent_t ev_after_plan);
 uint32_t sort_parts(uint32_t capacity);
+uint32_t sort_passes_for(uint32_t end_bit);
 cudaError_t init_sort_attributes();
 
 struct RasterLaunch {
-    const uint64_t* keys[2];
-    const uint32_t* vals[2];
-    const SortPlan* plan;
+    const uint64_t* keys[2];              // words tile << 32 | index, sorted
+    const SortPlan* plan;                 // of the tile sort
     const SplatGeo* geo;
     const float4* color;
+    const float2* depth_radius;
     uint32_t* ranges;                     // zeroed, tiles x 2
     uint8_t* out;
     size_t pitch;
-    uint32_t capacity;
     uint32_t width, height;
 };
-cudaError_t launch_ranges(const RasterLaunch& a, cudaStream_t s);
+cudaError_t launch_ranges(const RasterLaunch& a, uint32_t capacity, cudaStream_t s);
 cudaError_t launch_blend(const RasterLaunch& a, cudaStream_t s);
 
-cudaError_t launch_sort_unpack(const SortLaunch& a, uint64_t* out_keys, uint32_t* out_vals, cudaStream_t s);
+// introspection: sorted words -> the reference's (tile << 32 | depth bits, index) arrays
+cudaError_t launch_sort_unpack(const RasterLaunch& a, uint64_t* out_keys, uint32_t* out_vals, int sm_count, cudaStream_t s);
 cudaError_t launch_sort_copy_result(const SortLaunch& a, uint64_t* out_keys, uint32_t* out_vals, uint32_t n, cudaStream_t s);
 
 cudaError_t launch_export_splats(const SplatArrays& a, uint32_t n, void* out48, cudaStream_t s);

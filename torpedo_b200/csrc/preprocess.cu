@@ -170,15 +170,38 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t flag, uint32_t visible, u
 }
 constexpr uint64_t DESC_VALUE_MASK = (1ull << 62) - 1ull;
 
+// Decoupled look-back of a chained scan (one warp): exclusive prefix of partition `part` (> 0) over descriptors that carry
+// [63:62] state | [61:0] value. 32 predecessors are inspected per round.
+__device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* desc, uint32_t part, uint32_t lane) {
+    uint64_t exclusive = 0;
+    int look = (int)part - 1;
+    while (true) {
+        const int idx = look - (int)lane;
+        uint64_t d = ((uint64_t)FLAG_PREFIX << 62);  // virtual partition -1: inclusive prefix 0
+        if (idx >= 0) {
+            do { d = ld_relaxed_u64(desc + idx); } while ((d >> 62) == FLAG_INVALID);
+        }
+        const uint32_t prefix_mask = __ballot_sync(0xffffffffu, (d >> 62) == FLAG_PREFIX);
+        const uint32_t first = prefix_mask ? (uint32_t)__ffs((int)prefix_mask) - 1u : 32u;
+        uint64_t v = (lane <= first) ? (d & DESC_VALUE_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        exclusive += v;
+        if (prefix_mask) break;
+        look -= 32;
+    }
+    return exclusive;
+}
+
 struct Projected {
-    uint32_t count, rect_xy, rect_w, depth_bits;
+    uint32_t count, depth_bits;
 };
 
-// project.slang:33-90 for one Gaussian (colour excluded). Writes SplatGeo / depth_radius when visible.
+// project.slang:33-90 for one Gaussian (colour excluded). Writes SplatGeo / depth_radius / rect when visible.
 __device__ __forceinline__ Projected project_one(const PreprocessLaunch& a, uint32_t i, const float4 po, const float4 ca, const float2 cb,
                                                  const float* VM, const float* PM, const float* V, const float* focal, uint32_t gx,
                                                  uint32_t gy) {
-    Projected out{ 0u, 0u, 0u, 0u };
+    Projected out{ 0u, 0u };
     // splat/common.slang:98-119 passFrustumClipping
     auto row_point = [&](const float* m, int r) {
         return ((m[r * 4 + 0] * po.x + m[r * 4 + 1] * po.y) + m[r * 4 + 2] * po.z) + m[r * 4 + 3];
@@ -233,9 +256,8 @@ __device__ __forceinline__ Projected project_one(const PreprocessLaunch& a, uint
     const int y1 = min((int)gy, max(0, __float2int_rz((((py + radius) + 16.0f) - 1.0f) / 16.0f)));
     out.count = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
     if (out.count == 0) return out;
-    out.rect_xy = (uint32_t)x0 | ((uint32_t)y0 << 16);
-    out.rect_w = (uint32_t)(x1 - x0);
     out.depth_bits = __float_as_uint(vz);
+    a.out.rect[i] = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)(x1 - x0) | ((uint32_t)(y1 - y0) << 16));
 
     // Conservative half-extents of the region where alpha = opacity*exp(power) can reach 1/255 (blend.slang:88-89):
     // power >= -t, t = ln(255*opacity), is the ellipse d^T conic d <= 2t whose bounding box is sqrt(2t*cov). Used ONLY to
@@ -258,14 +280,13 @@ __device__ __forceinline__ Projected project_one(const PreprocessLaunch& a, uint
 }
 
 // One CTA = one partition of PRE_PART consecutive Gaussians (PRE_ITEMS per thread, striped so that loads coalesce).
+// Besides the per-Gaussian records it compacts the visible Gaussians, in index order, into `depth_words`
+// (float_bits(viewZ) << 32 | index): the input of the depth sort. The (visible, pairs) scan also yields the reference's
+// pair offsets (prefix.slang) and P.
 __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLaunch a) {
     __shared__ uint32_t s_part;
     __shared__ uint64_t s_base;                 // exclusive (visible, pairs) prefix of this partition
     __shared__ float s_vm[16], s_pm[16], s_v[12], s_focal[2];
-    __shared__ uint32_t s_off[PRE_PART];        // exclusive pair offsets inside the partition
-    __shared__ uint32_t s_xy[PRE_PART];         // rect origin: x0 | y0 << 16
-    __shared__ uint32_t s_w[PRE_PART];          // rect width
-    __shared__ uint32_t s_depth[PRE_PART];      // float bits of viewZ
     __shared__ uint64_t s_warp_tot[PRE_ITEMS][PRE_THREADS / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -298,7 +319,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
 #pragma unroll
     for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
         const uint32_t i = first + k * PRE_THREADS;
-        pr[k] = Projected{ 0u, 0u, 0u, 0u };
+        pr[k] = Projected{ 0u, 0u };
         if (i < n) {
             if (single_entity) {
                 pr[k] = project_one(a, i, po[k], ca[k], cb[k], s_vm, s_pm, s_v, s_focal, gx, gy);
@@ -312,7 +333,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
         }
     }
 
-    // ---- depth range of the frame (drives the sort's key compaction, sort.cu KeyXform) --------------------------------
+    // ---- depth range of the frame (the depth sort only sorts the bits this range occupies, sort.cu sort_spec) ---------
     {
         uint32_t dmin = 0xffffffffu, dmax = 0u;
 #pragma unroll
@@ -338,14 +359,10 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
             if (lane >= (uint32_t)d) incl[k] += up;
         }
         if (lane == 31) s_warp_tot[k][warp] = incl[k];
-        const uint32_t slot = k * PRE_THREADS + tid;
-        s_xy[slot] = pr[k].rect_xy;
-        s_w[slot] = pr[k].rect_w;
-        s_depth[slot] = pr[k].depth_bits;
     }
     __syncthreads();
     uint64_t total = 0;  // running (visible, pairs) total of the groups handled so far
-    uint32_t local_excl[PRE_ITEMS];
+    uint64_t local_excl[PRE_ITEMS];
 #pragma unroll
     for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
         uint64_t warp_excl = 0, group_total = 0;
@@ -355,8 +372,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
             if (w < warp) warp_excl += t;
             group_total += t;
         }
-        local_excl[k] = (uint32_t)(total + warp_excl + incl[k] - mine[k]);
-        s_off[k * PRE_THREADS + tid] = local_excl[k];
+        local_excl[k] = total + warp_excl + incl[k] - mine[k];
         total += group_total;
     }
 
@@ -368,22 +384,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
             if (lane == 0) st_relaxed_u64(a.scan_desc, ((uint64_t)FLAG_PREFIX << 62) | total);
         } else {
             if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_AGGREGATE << 62) | total);
-            int look = (int)part - 1;
-            while (true) {
-                const int idx = look - (int)lane;
-                uint64_t d = ((uint64_t)FLAG_PREFIX << 62);  // virtual partition -1: inclusive prefix 0
-                if (idx >= 0) {
-                    do { d = ld_relaxed_u64(a.scan_desc + idx); } while ((d >> 62) == FLAG_INVALID);
-                }
-                const uint32_t prefix_mask = __ballot_sync(0xffffffffu, (d >> 62) == FLAG_PREFIX);
-                const uint32_t first = prefix_mask ? (uint32_t)__ffs((int)prefix_mask) - 1u : 32u;
-                uint64_t v = (lane <= first) ? (d & DESC_VALUE_MASK) : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                exclusive += v;
-                if (prefix_mask) break;
-                look -= 32;
-            }
+            exclusive = lookback_exclusive(a.scan_desc, part, lane);
             if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_PREFIX << 62) | (exclusive + total));
         }
         if (lane == 0) {
@@ -397,71 +398,14 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
         }
     }
     __syncthreads();
-    const uint32_t base = (uint32_t)s_base;
+    const uint64_t base = s_base;
 #pragma unroll
-    for (uint32_t k = 0; k < PRE_ITEMS; ++k)
-        if (first + k * PRE_THREADS < n) a.out.offsets[first + k * PRE_THREADS] = base + local_excl[k];
-
-    // ---- duplication (keygen.slang:47-53): the partition's pairs are emitted cooperatively ----------------------------
-    // Each thread takes groups of four CONSECUTIVE global slots (aligned to 4, so a full group is two 16-byte key stores
-    // and one 16-byte value store): one binary search finds the Gaussian owning the first slot, the next slots walk
-    // forward — the next tile of the same rectangle (x+1, wrapping to the next row) or the first tile of the next visible
-    // Gaussian. The reference loops serially per Gaussian; here big and small splats cost the same per pair.
-    const uint32_t part_pairs = (uint32_t)total;
-    const uint32_t slot_end = base + part_pairs;
-    const uint32_t id_base = part * PRE_PART;
-    for (uint32_t G0 = (base & ~3u) + 4u * tid; G0 < slot_end; G0 += 4u * PRE_THREADS) {
-        const uint32_t lo = max(G0, base), hi = min(G0 + 4u, slot_end);  // valid global slots of this group: [lo, hi)
-        const uint32_t j = lo - base;
-        uint32_t g = 0;
-#pragma unroll
-        for (uint32_t step = PRE_PART / 2; step >= 1; step >>= 1)
-            if (s_off[g + step] <= j) g += step;
-        uint32_t w = s_w[g], xy = s_xy[g], depth = s_depth[g];
-        const uint32_t r = j - s_off[g];
-        const uint32_t ry = r / w;
-        uint32_t rx = r - ry * w;
-        uint32_t row = ((xy >> 16) + ry) * gx + (xy & 0xffffu);  // tile id of the rectangle's column 0 in the current row
-        uint32_t next_off = g + 1 < PRE_PART ? s_off[g + 1] : 0xffffffffu;
-        uint64_t key[4];
-        uint32_t val[4];
-#pragma unroll
-        for (uint32_t q = 0; q < 4; ++q) {
-            const uint32_t G = G0 + q;
-            if (G >= lo && G < hi) {
-                if (G > lo) {
-                    const uint32_t jq = G - base;
-                    if (jq >= next_off) {  // first tile of the next visible Gaussian (zero-count ones share their offset)
-                        do {
-                            ++g;
-                            next_off = g + 1 < PRE_PART ? s_off[g + 1] : 0xffffffffu;
-                        } while (jq >= next_off);
-                        w = s_w[g]; xy = s_xy[g]; depth = s_depth[g];
-                        rx = 0;
-                        row = (xy >> 16) * gx + (xy & 0xffffu);
-                    } else if (++rx == w) {
-                        rx = 0;
-                        row += gx;
-                    }
-                }
-                key[q] = ((uint64_t)(row + rx) << 32) | depth;
-                val[q] = id_base + g;
-            }
-        }
-        if (lo == G0 && hi == G0 + 4u && G0 + 4u <= a.capacity) {
-            ulonglong2* kp = reinterpret_cast<ulonglong2*>(a.keys + G0);
-            kp[0] = make_ulonglong2(key[0], key[1]);
-            kp[1] = make_ulonglong2(key[2], key[3]);
-            *reinterpret_cast<uint4*>(a.vals + G0) = make_uint4(val[0], val[1], val[2], val[3]);
-        } else {
-#pragma unroll
-            for (uint32_t q = 0; q < 4; ++q) {
-                const uint32_t G = G0 + q;
-                if (G >= lo && G < hi && G < a.capacity) {
-                    a.keys[G] = key[q];
-                    a.vals[G] = val[q];
-                }
-            }
+    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
+        const uint32_t i = first + k * PRE_THREADS;
+        if (i < n) {
+            const uint64_t at = base + local_excl[k];
+            a.out.offsets[i] = (uint32_t)at;
+            if (pr[k].count != 0) a.depth_words[(uint32_t)(at >> 32)] = ((uint64_t)pr[k].depth_bits << 32) | i;
         }
     }
 }
@@ -469,6 +413,158 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
 cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s) {
     if (a.scene.n == 0) return cudaSuccess;
     preprocess_kernel<<<(a.scene.n + PRE_PART - 1) / PRE_PART, PRE_THREADS, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// duplication (keygen.slang:47-53) over the DEPTH-SORTED visible Gaussians
+// ---------------------------------------------------------------------------------------------------
+//
+// The reference emits the pairs of Gaussian i at offsets[i] (index order) and sorts them by tile << 32 | depth. Here the
+// visible Gaussians arrive sorted by (depth, index); emitting their pairs in that order makes the remaining work a stable
+// sort by tile only. One CTA = EMIT_PART consecutive sorted Gaussians: gather their rectangles, scan the tile counts
+// (chained look-back across CTAs for the global offset), then emit the CTA's pairs cooperatively.
+
+constexpr uint32_t EMIT_THREADS = 256;
+constexpr uint32_t EMIT_ITEMS = 4;
+constexpr uint32_t EMIT_PART = EMIT_THREADS * EMIT_ITEMS;
+
+__global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
+    __shared__ uint32_t s_part;
+    __shared__ uint64_t s_base;
+    __shared__ uint32_t s_off[EMIT_PART];       // exclusive pair offsets inside the partition
+    __shared__ uint32_t s_xy[EMIT_PART];        // rect origin: x0 | y0 << 16
+    __shared__ uint32_t s_w[EMIT_PART];         // rect width
+    __shared__ uint32_t s_id[EMIT_PART];        // Gaussian index
+    __shared__ uint32_t s_warp_tot[EMIT_ITEMS][EMIT_THREADS / 32];
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_part = atomicAdd(&a.ctl->emit_ticket, 1u);
+    __syncthreads();
+    const uint32_t part = s_part;
+    const uint32_t visible = a.depth_plan->n;
+    if ((uint64_t)part * EMIT_PART >= visible) return;
+    const uint64_t* __restrict__ sorted = a.depth_plan->final_sel ? a.depth_words[1] : a.depth_words[0];
+    const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX;
+
+    // ---- gather: blocked, so that a thread's EMIT_ITEMS Gaussians are consecutive in depth order -----------------------
+    uint32_t cnt[EMIT_ITEMS];
+#pragma unroll
+    for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
+        const uint32_t slot = k * EMIT_THREADS + tid;           // striped loads (coalesced), partition order = slot order
+        const uint32_t r = part * EMIT_PART + slot;
+        uint32_t id = 0;
+        uint2 rc = make_uint2(0u, 0u);
+        if (r < visible) {
+            id = (uint32_t)__ldg(sorted + r);
+            rc = __ldg(a.rect + id);
+        }
+        cnt[k] = (rc.y & 0xffffu) * (rc.y >> 16);
+        s_xy[slot] = rc.x;
+        s_w[slot] = rc.y & 0xffffu;
+        s_id[slot] = id;
+    }
+
+    // ---- partition-local exclusive scan of the tile counts; group k = slots [k*256, (k+1)*256) -------------------------
+    uint32_t incl[EMIT_ITEMS];
+#pragma unroll
+    for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
+        incl[k] = cnt[k];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl[k], d);
+            if (lane >= (uint32_t)d) incl[k] += up;
+        }
+        if (lane == 31) s_warp_tot[k][warp] = incl[k];
+    }
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
+        uint32_t warp_excl = 0, group_total = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < EMIT_THREADS / 32; ++w) {
+            const uint32_t t = s_warp_tot[k][w];
+            if (w < warp) warp_excl += t;
+            group_total += t;
+        }
+        s_off[k * EMIT_THREADS + tid] = total + warp_excl + incl[k] - cnt[k];
+        total += group_total;
+    }
+
+    // ---- decoupled look-back across partitions (warp 0) ---------------------------------------------
+    if (warp == 0) {
+        uint64_t exclusive = 0;
+        if (part == 0) {
+            if (lane == 0) st_relaxed_u64(a.scan_desc, ((uint64_t)FLAG_PREFIX << 62) | total);
+        } else {
+            if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_AGGREGATE << 62) | total);
+            exclusive = lookback_exclusive(a.scan_desc, part, lane);
+            if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_PREFIX << 62) | (exclusive + total));
+        }
+        if (lane == 0) s_base = exclusive;
+    }
+    __syncthreads();
+    const uint32_t base = (uint32_t)s_base;
+
+    // ---- emission: each thread takes groups of four CONSECUTIVE global slots (aligned to 4, so a full group is two 16-byte
+    // stores): one binary search finds the Gaussian owning the first slot, the next slots walk forward — the next tile of the
+    // same rectangle (x+1, wrapping to the next row) or the first tile of the next Gaussian. The reference loops serially
+    // per Gaussian; here big and small splats cost the same per pair.
+    const uint32_t slot_end = base + total;
+    for (uint32_t G0 = (base & ~3u) + 4u * tid; G0 < slot_end; G0 += 4u * EMIT_THREADS) {
+        const uint32_t lo = max(G0, base), hi = min(G0 + 4u, slot_end);  // valid global slots of this group: [lo, hi)
+        const uint32_t j = lo - base;
+        uint32_t g = 0;
+#pragma unroll
+        for (uint32_t step = EMIT_PART / 2; step >= 1; step >>= 1)
+            if (s_off[g + step] <= j) g += step;
+        uint32_t w = s_w[g], xy = s_xy[g], id = s_id[g];
+        const uint32_t r = j - s_off[g];
+        const uint32_t ry = r / w;
+        uint32_t rx = r - ry * w;
+        uint32_t row = ((xy >> 16) + ry) * gx + (xy & 0xffffu);  // tile id of the rectangle's column 0 in the current row
+        uint32_t next_off = g + 1 < EMIT_PART ? s_off[g + 1] : 0xffffffffu;
+        uint64_t key[4];
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            const uint32_t G = G0 + q;
+            if (G >= lo && G < hi) {
+                if (G > lo) {
+                    const uint32_t jq = G - base;
+                    if (jq >= next_off) {  // first tile of the next Gaussian (padding slots of the last partition share their offset)
+                        do {
+                            ++g;
+                            next_off = g + 1 < EMIT_PART ? s_off[g + 1] : 0xffffffffu;
+                        } while (jq >= next_off);
+                        w = s_w[g]; xy = s_xy[g]; id = s_id[g];
+                        rx = 0;
+                        row = (xy >> 16) * gx + (xy & 0xffffu);
+                    } else if (++rx == w) {
+                        rx = 0;
+                        row += gx;
+                    }
+                }
+                key[q] = ((uint64_t)(row + rx) << 32) | id;
+            }
+        }
+        if (lo == G0 && hi == G0 + 4u && G0 + 4u <= a.capacity) {
+            ulonglong2* kp = reinterpret_cast<ulonglong2*>(a.keys + G0);
+            kp[0] = make_ulonglong2(key[0], key[1]);
+            kp[1] = make_ulonglong2(key[2], key[3]);
+        } else {
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                const uint32_t G = G0 + q;
+                if (G >= lo && G < hi && G < a.capacity) a.keys[G] = key[q];
+            }
+        }
+    }
+}
+
+cudaError_t launch_emit(const EmitLaunch& a, cudaStream_t s) {
+    if (a.n == 0) return cudaSuccess;
+    emit_kernel<<<(a.n + EMIT_PART - 1) / EMIT_PART, EMIT_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -534,6 +630,30 @@ __global__ void export_splats_kernel(SplatArrays a, uint32_t n, uint32_t* out) {
     o[4] = __float_as_uint(r.px); o[5] = __float_as_uint(r.py); o[6] = __float_as_uint(zr.x); o[7] = __float_as_uint(zr.y);
     o[8] = __float_as_uint(r.conic_a); o[9] = __float_as_uint(r.conic_b); o[10] = __float_as_uint(r.conic_c);
     o[11] = __float_as_uint(r.opacity);
+}
+
+// The reference's unsorted key/value buffers (keygen.slang:47-53): Gaussian i writes its tiles row-major at offsets[i].
+__global__ void export_unsorted_kernel(SplatArrays a, uint32_t n, uint32_t gx, uint64_t* keys, uint32_t* vals, uint32_t capacity) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t off = a.offsets[i];
+    if (a.offsets[i + 1] == off) return;
+    const uint2 rc = a.rect[i];
+    const uint32_t depth = __float_as_uint(a.depth_radius[i].x);
+    const uint32_t x0 = rc.x & 0xffffu, y0 = rc.x >> 16, w = rc.y & 0xffffu, h = rc.y >> 16;
+    for (uint32_t y = y0; y < y0 + h; ++y)
+        for (uint32_t x = x0; x < x0 + w; ++x, ++off)
+            if (off < capacity) {
+                keys[off] = ((uint64_t)(y * gx + x) << 32) | depth;
+                vals[off] = i;
+            }
+}
+
+cudaError_t launch_export_unsorted(const SplatArrays& a, uint32_t n, uint32_t width, uint64_t* keys, uint32_t* vals, uint32_t capacity,
+                                   cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    export_unsorted_kernel<<<(n + 255) / 256, 256, 0, s>>>(a, n, (width + TILE_PX - 1) / TILE_PX, keys, vals, capacity);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_export_splats(const SplatArrays& a, uint32_t n, void* out48, cudaStream_t s) {

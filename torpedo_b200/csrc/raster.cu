@@ -9,14 +9,13 @@
 namespace tpdcu {
 
 // ---------------------------------------------------------------------------------------------------
-// ranges: ranges[tile] = (first, last+1) over the sorted keys; empty tiles stay (0,0)
+// ranges: ranges[tile] = (first, last+1) over the sorted words; empty tiles stay (0,0)
 // ---------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
     const uint32_t n = a.plan->n;
-    if (a.plan->packed_overflow) return;  // this frame is going to be re-rendered in pair mode
     const uint64_t* __restrict__ keys = a.plan->final_sel ? a.keys[1] : a.keys[0];
-    const uint32_t tshift = a.plan->packed ? a.plan->depth_bits + a.plan->idx_bits : 32u;  // tile id sits on top in both formats
+    constexpr uint32_t tshift = 32u;  // words are tile << 32 | Gaussian index
     uint2* ranges = reinterpret_cast<uint2*>(a.ranges);
     // two keys per thread with one 16-byte load; the key before the pair comes from the neighbour's line (L1 hit)
     const uint32_t pairs2 = (n + 1) / 2;
@@ -47,9 +46,9 @@ __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
     }
 }
 
-cudaError_t launch_ranges(const RasterLaunch& a, cudaStream_t s) {
-    if (a.capacity == 0) return cudaSuccess;
-    uint32_t grid = (a.capacity / 2 + 255) / 256;
+cudaError_t launch_ranges(const RasterLaunch& a, uint32_t capacity, cudaStream_t s) {
+    if (capacity == 0) return cudaSuccess;
+    uint32_t grid = (capacity / 2 + 255) / 256;
     if (grid > 148u * 8u) grid = 148u * 8u;
     ranges_kernel<<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
@@ -125,10 +124,6 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
     asm volatile("" : "+f"(fx0), "+f"(fy0));  // keep the pixel coordinates in registers: do not re-convert them per splat
     const float tile_fx0 = (float)tile_x0, tile_fy0 = (float)tile_y0;
 
-    if (a.plan->packed_overflow) return;  // this frame is going to be re-rendered in pair mode
-    const bool packed = a.plan->packed != 0u;
-    const uint32_t idx_mask = packed ? (uint32_t)((1ull << a.plan->idx_bits) - 1ull) : 0xffffffffu;
-    const uint32_t* __restrict__ vals = a.plan->final_sel ? a.vals[1] : a.vals[0];
     const uint64_t* __restrict__ words = a.plan->final_sel ? a.keys[1] : a.keys[0];
     const uint2 range = reinterpret_cast<const uint2*>(a.ranges)[tile];
     const float4* __restrict__ geo4 = reinterpret_cast<const float4*>(a.geo);
@@ -162,7 +157,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
             uint32_t g = 0;
             float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
             if (idx < range.y) {
-                g = packed ? ((uint32_t)__ldg(words + idx) & idx_mask) : __ldg(vals + idx);
+                g = (uint32_t)__ldg(words + idx);
                 ra = __ldg(geo4 + (size_t)g * 2);
                 rb = __ldg(geo4 + (size_t)g * 2 + 1);
                 const float xlo = ra.x - rb.z - tile_fx0, xhi = ra.x + rb.z - tile_fx0;  // bbox relative to the tile origin

@@ -1,14 +1,18 @@
-// sort.cu — stable 64-bit-key / 32-bit-value LSD radix sort in the onesweep style
-// (one up-front multi-digit histogram, then ONE read + ONE write of every pair per 8-bit digit,
-// with a chained decoupled look-back across tiles instead of a separate scan per pass).
+// sort.cu — stable LSD radix sort in the onesweep style (one up-front multi-digit histogram, then ONE read + ONE write
+// of every element per 8-bit digit, with a chained decoupled look-back across tiles instead of a separate scan per pass).
 //
 // Replaces the reference's 4-way radix sorter: radix-shuffle.slang:37-150, radix-prefixA.slang:37-169,
-// radix-prefixB.slang:37-168, radix-mapping.slang:38-116 driven by GaussianEngine.cpp:822-841
-// (23 passes x 4 dispatches at 1080p, ~1.1 KB of DRAM traffic per pair) with
-// ceil(end_bit/8) passes (6 at 1080p) of 24 B per pair each, + 8 B per pair for the histogram.
+// radix-prefixB.slang:37-168, radix-mapping.slang:38-116 driven by GaussianEngine.cpp:822-841 (23 passes x 4 dispatches
+// over every (tile | depth, index) pair at 1080p, ~1.1 KB of DRAM traffic per pair).
 //
-// The number of pairs lives in device memory (FrameCtl::pairs_total): the host never learns P inside a
-// frame, grids are sized by the buffer capacity and surplus CTAs exit on their ticket.
+// A frame sorts in two levels (tpdcu.cu): the VISIBLE GAUSSIANS by depth (words depth << 32 | index, <= 4 passes over
+// ~n elements), then — after the duplication stage has emitted the pairs in that order — the PAIRS by tile (words
+// tile << 32 | index, ceil(tile_bits / 8) = 2 passes at 1080p). Both sorts are stable and the index rides in the low half
+// of the word, so the result is exactly the reference's stable sort of (tile << 32 | depth, index) pairs, for
+// 8 + 2 * 16 B of traffic per pair instead of 8 + 5 * 16 + 4.
+//
+// Element counts live in device memory (FrameCtl): the host never learns them inside a frame, grids are sized by the
+// buffer capacities and surplus CTAs exit on their ticket. The standalone API sorts caller-provided (u64, u32) pairs.
 #include "common.cuh"
 
 namespace tpdcu {
@@ -20,59 +24,56 @@ constexpr uint32_t LOOKBACK_BATCH = 8;
 #ifndef TPDCU_SORT_PREFETCH_TILES
 #define TPDCU_SORT_PREFETCH_TILES 296
 #endif
-#ifndef TPDCU_SORT_MINB_PACKED
-#define TPDCU_SORT_MINB_PACKED 4
+#ifndef TPDCU_SORT_MINB_WORDS
+#define TPDCU_SORT_MINB_WORDS 4
 #endif
 constexpr uint32_t SORT_PREFETCH_TILES = TPDCU_SORT_PREFETCH_TILES;  // 148 SMs x 3 resident CTAs
 
-// Order-preserving key compaction (frame path): keys are tile << 32 | float_bits(viewZ) with viewZ confined to
-// [min, max] of the frame, so the passes sort on  tile << depth_bits | (depth - min)  instead — at 1080p with the default
-// near/far planes that is 27 + 13 = 40 bits = 5 passes instead of 6. The stored keys are never modified.
-struct KeyXform {
-    uint32_t bias, depth_bits, total_bits;
+// What a sort launch works on (see SORT_KIND_* in common.cuh); derived on the device because n and the depth range are.
+struct SortSpec {
+    uint32_t n, bias, total_bits;
 };
-__device__ __forceinline__ KeyXform make_xform(uint32_t depth_min, uint32_t depth_max, uint32_t end_bit, bool frame_keys) {
-    KeyXform x;
-    if (!frame_keys) { x.bias = 0; x.depth_bits = min(end_bit, 32u); x.total_bits = end_bit; return x; }
-    x.bias = depth_max >= depth_min ? depth_min : 0u;
-    const uint32_t span = depth_max >= depth_min ? depth_max - depth_min : 0u;
-    x.depth_bits = 32u - __clz(span);           // 0 when every key carries the same depth
-    x.total_bits = x.depth_bits + (end_bit - 32u);
+__device__ __forceinline__ SortSpec sort_spec(const FrameCtl* fr, uint32_t kind, uint32_t n_host, uint32_t capacity, uint32_t end_bit) {
+    SortSpec x;
+    if (kind == SORT_KIND_PAIRS) {
+        x.n = n_host; x.bias = 0; x.total_bits = end_bit;
+    } else if (kind == SORT_KIND_DEPTH) {
+        const uint32_t dmin = ~fr->inv_depth_min, dmax = fr->depth_max;
+        x.n = min(fr->visible, capacity);
+        x.bias = dmax >= dmin ? dmin : 0u;
+        x.total_bits = dmax >= dmin ? 32u - __clz(dmax - dmin) : 0u;  // 0 when every Gaussian carries the same depth
+    } else {
+        x.n = min(fr->pairs_total, capacity); x.bias = 0; x.total_bits = end_bit;
+    }
     return x;
 }
-__device__ __forceinline__ uint32_t digit_of(uint64_t key, const KeyXform& x, uint32_t shift, uint32_t mask) {
-    const uint32_t lo = (uint32_t)key - x.bias, hi = (uint32_t)(key >> 32);
-    const uint64_t packed = x.depth_bits >= 32u ? (((uint64_t)hi << 32) | lo) : (((uint64_t)hi << x.depth_bits) | lo);
-    return (uint32_t)(packed >> shift) & mask;
-}
-__device__ __forceinline__ uint64_t pack_word(uint64_t key, uint32_t val, const KeyXform& x, uint32_t idx_bits) {
-    const uint32_t lo = (uint32_t)key - x.bias, hi = (uint32_t)(key >> 32);
-    const uint64_t packed = x.depth_bits >= 32u ? (((uint64_t)hi << 32) | lo) : (((uint64_t)hi << x.depth_bits) | lo);
-    return (packed << idx_bits) | val;
+// the 64-bit quantity whose bits [0, total_bits) are sorted
+template <bool WORDS>
+__device__ __forceinline__ uint64_t sort_key(uint64_t k, uint32_t bias) {
+    return WORDS ? (uint64_t)((uint32_t)(k >> 32) - bias) : k;
 }
 
 __device__ __forceinline__ uint32_t pass_mask(uint32_t pass, uint32_t total_bits) {
     const uint32_t left = total_bits > pass * SORT_RADIX_BITS ? total_bits - pass * SORT_RADIX_BITS : 0u;
     return left >= SORT_RADIX_BITS ? (SORT_BINS - 1u) : ((1u << left) - 1u);
 }
-__device__ __forceinline__ uint32_t passes_needed(uint32_t total_bits) { return (total_bits + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS; }
+__host__ __device__ __forceinline__ uint32_t passes_needed(uint32_t total_bits) { return (total_bits + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS; }
 
 // ---------------------------------------------------------------------------------------------------
 // up-front histogram of every digit (one read of the keys)
 // ---------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t* __restrict__ keys, FrameCtl* ctl,
-                                                                  uint32_t n_host, uint32_t capacity, uint32_t num_passes,
-                                                                  uint32_t end_bit) {
+template <bool WORDS>
+__global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t* __restrict__ keys, const FrameCtl* frame, SortCtl* ctl,
+                                                                  uint32_t kind, uint32_t n_host, uint32_t capacity, uint32_t end_bit) {
     __shared__ uint32_t h[SORT_MAX_PASSES][SORT_BINS];
-    const uint32_t n = n_host == UINT32_MAX ? min(ctl->pairs_total, capacity) : n_host;
-    const KeyXform xf = make_xform(~ctl->inv_depth_min, ctl->depth_max, end_bit, n_host == UINT32_MAX);
-    num_passes = min(num_passes, passes_needed(xf.total_bits));  // passes above the packed key width see a single bin
+    const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit);
+    const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
     for (uint32_t k = threadIdx.x; k < num_passes * SORT_BINS; k += HIST_THREADS) (&h[0][0])[k] = 0;
     __syncthreads();
-    // Each thread takes HIST_KPT CONSECUTIVE keys (four 16-byte loads): the pairs of one Gaussian are adjacent in the
-    // unsorted buffer and share their depth bits (and usually the upper tile bits), so run-length encoding the digits in
-    // registers removes most shared-memory atomics and nearly all same-address conflicts.
+    // Each thread takes HIST_KPT CONSECUTIVE elements (four 16-byte loads): the pairs of one Gaussian are adjacent in the
+    // unsorted buffer and usually share the upper tile bits, so run-length encoding the digits in registers removes most
+    // shared-memory atomics and nearly all same-address conflicts.
     const uint32_t chunk = HIST_THREADS * HIST_KPT;
     for (uint32_t base = blockIdx.x * chunk; base < n; base += gridDim.x * chunk) {
         const uint32_t first = base + threadIdx.x * HIST_KPT;
@@ -91,9 +92,9 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
         const uint32_t valid = first >= n ? 0u : min(HIST_KPT, n - first);
         if (valid) {
 #pragma unroll
-            for (uint32_t j = 0; j < HIST_KPT; ++j) k[j] = pack_word(k[j], 0u, xf, 0u);  // tile << depth_bits | depth - bias, once per key
+            for (uint32_t j = 0; j < HIST_KPT; ++j) k[j] = sort_key<WORDS>(k[j], sp.bias);
             for (uint32_t p = 0; p < num_passes; ++p) {
-                const uint32_t shift = p * SORT_RADIX_BITS, mask = pass_mask(p, xf.total_bits);
+                const uint32_t shift = p * SORT_RADIX_BITS, mask = pass_mask(p, sp.total_bits);
                 uint32_t run_digit = (uint32_t)(k[0] >> shift) & mask, run = 1;
 #pragma unroll
                 for (uint32_t j = 1; j < HIST_KPT; ++j) {
@@ -122,14 +123,13 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
 // plan: exclusive digit offsets, identity-pass detection, ping-pong schedule
 // ---------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, SortPlan* plan, uint32_t n_host, uint32_t capacity,
-                                                               uint32_t num_passes, uint32_t end_bit, uint32_t packed_idx_bits, uint32_t packed_word_bits) {
+__global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(const FrameCtl* frame, SortCtl* ctl, SortPlan* plan, uint32_t kind,
+                                                               uint32_t n_host, uint32_t capacity, uint32_t end_bit) {
     __shared__ uint32_t s_warp[SORT_BINS / 32];
     __shared__ uint32_t s_skip[SORT_MAX_PASSES];
-    const uint32_t n = n_host == UINT32_MAX ? min(ctl->pairs_total, capacity) : n_host;
+    const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit);
+    const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
     const uint32_t b = threadIdx.x, lane = b & 31u, warp = b >> 5;
-    const KeyXform xf = make_xform(~ctl->inv_depth_min, ctl->depth_max, end_bit, n_host == UINT32_MAX);
-    num_passes = min(num_passes, passes_needed(xf.total_bits));
     if (b < SORT_MAX_PASSES) s_skip[b] = 0;
     __syncthreads();
     for (uint32_t p = 0; p < num_passes; ++p) {
@@ -150,10 +150,8 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, Sor
     }
     if (b == 0) {
         uint32_t sel = 0, run = 0;
-        const bool packed = packed_idx_bits != 0u;
         for (uint32_t p = 0; p < SORT_MAX_PASSES; ++p) {
-            uint32_t skip = p < num_passes ? s_skip[p] : 1u;
-            if (packed && p == 0 && n > 0) skip = 0;  // the first pass also converts pairs to packed words: never skipped
+            const uint32_t skip = p < num_passes ? s_skip[p] : 1u;
             plan->skip[p] = skip;
             plan->src_sel[p] = sel;
             if (!skip) { sel ^= 1u; ++run; }
@@ -162,13 +160,8 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, Sor
         plan->num_passes = num_passes;
         plan->final_sel = sel;
         plan->passes_run = run;
-        plan->bias = xf.bias;
-        plan->depth_bits = xf.depth_bits;
-        plan->total_bits = xf.total_bits;
-        plan->idx_bits = packed ? packed_idx_bits : 0u;
-        plan->packed = packed ? 1u : 0u;
-        // a packed word must hold tile | depth - bias | index; if this frame's depth range is too wide the host re-renders in pair mode
-        plan->packed_overflow = (packed && xf.total_bits + packed_idx_bits > packed_word_bits) ? 1u : 0u;
+        plan->bias = sp.bias;
+        plan->total_bits = sp.total_bits;
     }
 }
 
@@ -176,12 +169,10 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(FrameCtl* ctl, Sor
 // one onesweep pass
 // ---------------------------------------------------------------------------------------------------
 
-// Sort modes. PAIRS: (u64 key, u32 value) in and out (standalone API, fallback). PACK: pairs in, single 64-bit words out
-// (first pass of a frame). PACKED: words in and out. A word is  tile << (depth_bits+idx_bits) | (depth-bias) << idx_bits | index:
-// the Gaussian index rides in the low bits of the key, so a pass moves 16 B per pair instead of 24 B, the value scatter
-// through shared memory disappears, and — pairs being emitted in ascending index order — sorting the bits above idx_bits
-// stably is exactly the reference's stable sort of (key, value) pairs.
-enum : int { MODE_PAIRS = 0, MODE_PACK = 1, MODE_PACKED = 2 };
+// Sort modes. PAIRS: (u64 key, u32 value) in and out (standalone API). WORDS: single 64-bit words whose high half is the
+// key and whose low half (the Gaussian index) is payload: a pass moves 16 B per element instead of 24 B and the value
+// scatter through shared memory disappears.
+enum : int { MODE_PAIRS = 0, MODE_WORDS = 1 };
 
 template <bool WITH_VALS>
 struct OnesweepSmem {
@@ -198,10 +189,10 @@ static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phas
 //   ticket + zero per-warp histograms | load keys, early counts | per-bin: warp prefix, publish aggregate, bin scan |
 //   stable ranking (match.any) + scatter to smem | look-back per bin | coalesced write-out (+ value scatter / write-out)
 template <int MODE>
-__global__ void __launch_bounds__(SORT_THREADS, MODE == MODE_PACKED ? TPDCU_SORT_MINB_PACKED : TPDCU_SORT_MINB)
-onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, FrameCtl* ctl,
+__global__ void __launch_bounds__(SORT_THREADS, MODE == MODE_WORDS ? TPDCU_SORT_MINB_WORDS : TPDCU_SORT_MINB)
+onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, SortCtl* ctl,
                 const SortPlan* __restrict__ plan, uint32_t* lookback_pass, uint32_t pass) {
-    constexpr bool IN_PAIRS = MODE != MODE_PACKED, OUT_PAIRS = MODE == MODE_PAIRS;
+    constexpr bool IN_PAIRS = MODE == MODE_PAIRS, OUT_PAIRS = MODE == MODE_PAIRS, WORDS = MODE == MODE_WORDS;
     using Smem = OnesweepSmem<OUT_PAIRS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -209,7 +200,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     if (plan->skip[pass]) return;
     const uint32_t n = plan->n;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) sm.part = atomicAdd(&ctl->sort_ticket[pass], 1u);
+    if (tid == 0) sm.part = atomicAdd(&ctl->ticket[pass], 1u);
     {
         uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[0][0]);
 #pragma unroll
@@ -238,12 +229,10 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_vals + ahead), "r"((uint32_t)(SORT_TILE * sizeof(uint32_t))) : "memory");
         }
     }
-    const KeyXform xf{ plan->bias, plan->depth_bits, plan->total_bits };
-    const uint32_t idx_bits = plan->idx_bits;
-    const uint32_t shift = pass * SORT_RADIX_BITS, mask = pass_mask(pass, xf.total_bits);
-    // digit of an INPUT element / of an element as it sits in shared memory (= output format)
-    auto digit_in = [&](uint64_t k) { return IN_PAIRS ? digit_of(k, xf, shift, mask) : ((uint32_t)(k >> (idx_bits + shift)) & mask); };
-    auto digit_out = [&](uint64_t k) { return OUT_PAIRS ? digit_of(k, xf, shift, mask) : ((uint32_t)(k >> (idx_bits + shift)) & mask); };
+    const uint32_t bias = plan->bias, total_bits = plan->total_bits;
+    const uint32_t shift = pass * SORT_RADIX_BITS, mask = pass_mask(pass, total_bits);
+    auto digit_in = [&](uint64_t k) { return (uint32_t)(sort_key<WORDS>(k, bias) >> shift) & mask; };
+    auto digit_out = digit_in;  // elements sit in shared memory in their input format
 
     // ---- load (warp-striped: item k of lane l sits at warp_base + 32k + l) --------------------------
     uint64_t key[SORT_KPT];
@@ -329,7 +318,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         __syncwarp();
         const uint32_t r = base + lower;
         if (OUT_PAIRS) rank[k] = r;
-        sm.keys[r] = MODE == MODE_PACK ? pack_word(key[k], val[k], xf, idx_bits) : key[k];
+        sm.keys[r] = key[k];
     }
 
     // ---- decoupled look-back, one thread per bin -----------------------------------------------------
@@ -386,17 +375,15 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     }
 }
 
-// introspection: packed words -> the reference's (key, value) arrays
-__global__ void sort_unpack_kernel(const uint64_t* keys0, const uint64_t* keys1, const SortPlan* plan, uint64_t* out_keys, uint32_t* out_vals) {
-    const uint64_t* w = plan->final_sel ? keys1 : keys0;
-    const uint32_t n = plan->n, ib = plan->idx_bits, db = plan->depth_bits, bias = plan->bias;
+// introspection: sorted words -> the reference's (tile << 32 | depth bits, index) arrays
+__global__ void sort_unpack_kernel(RasterLaunch a, uint64_t* out_keys, uint32_t* out_vals) {
+    const uint64_t* w = a.plan->final_sel ? a.keys[1] : a.keys[0];
+    const uint32_t n = a.plan->n;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint64_t x = w[i];
-        const uint64_t kp = x >> ib;
-        const uint32_t depth = (db >= 32u ? (uint32_t)kp : (uint32_t)(kp & ((1ull << db) - 1ull))) + bias;
-        const uint32_t tile = db >= 32u ? (uint32_t)(kp >> 32) : (uint32_t)(kp >> db);
-        out_keys[i] = ((uint64_t)tile << 32) | depth;
-        out_vals[i] = (uint32_t)(x & ((1ull << ib) - 1ull));
+        const uint32_t g = (uint32_t)x;
+        out_keys[i] = (x & 0xffffffff00000000ull) | __float_as_uint(a.depth_radius[g].x);
+        out_vals[i] = g;
     }
 }
 
@@ -412,6 +399,7 @@ __global__ void sort_copy_result_kernel(const uint64_t* keys1, const uint32_t* v
 }
 
 uint32_t sort_parts(uint32_t capacity) { return (capacity + SORT_TILE - 1) / SORT_TILE; }
+uint32_t sort_passes_for(uint32_t end_bit) { return passes_needed(end_bit); }
 
 template <int MODE>
 static cudaError_t set_smem_attr() {
@@ -422,17 +410,16 @@ static cudaError_t set_smem_attr() {
 // opt in to > 48 KB of dynamic shared memory; called once per context, outside any stream capture
 cudaError_t init_sort_attributes() {
     cudaError_t e = set_smem_attr<MODE_PAIRS>();
-    if (e == cudaSuccess) e = set_smem_attr<MODE_PACK>();
-    if (e == cudaSuccess) e = set_smem_attr<MODE_PACKED>();
+    if (e == cudaSuccess) e = set_smem_attr<MODE_WORDS>();
     return e;
 }
 
 cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cudaEvent_t ev_after_plan) {
-    const uint32_t num_passes = (a.end_bit + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS;
-    const uint32_t bound = n_host == UINT32_MAX ? a.capacity : n_host;
-    const uint32_t pib = a.packed_idx_bits;
+    const bool words = a.kind != SORT_KIND_PAIRS;
+    const uint32_t num_passes = passes_needed(a.end_bit);  // upper bound; the plan kernel marks the passes a frame does not need
+    const uint32_t bound = words ? a.capacity : n_host;
     if (bound == 0 || num_passes == 0) {
-        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host == UINT32_MAX ? UINT32_MAX : 0u, a.capacity, 0, a.end_bit, pib, a.packed_word_bits ? a.packed_word_bits : 64u);
+        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.frame, a.ctl, a.plan, bound == 0 ? (uint32_t)SORT_KIND_PAIRS : a.kind, 0u, a.capacity, 0u);
         if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
         return cudaGetLastError();
     }
@@ -440,25 +427,24 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     uint32_t hist_grid = (bound + chunk - 1) / chunk;
     const uint32_t hist_max = (uint32_t)a.sm_count * 4u;
     if (hist_grid > hist_max) hist_grid = hist_max;
-    sort_hist_kernel<<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.ctl, n_host, a.capacity, num_passes, a.end_bit);
-    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.ctl, a.plan, n_host, a.capacity, num_passes, a.end_bit, pib, a.packed_word_bits ? a.packed_word_bits : 64u);
+    if (words) sort_hist_kernel<true><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.kind, n_host, a.capacity, a.end_bit);
+    else sort_hist_kernel<false><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.kind, n_host, a.capacity, a.end_bit);
+    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit);
     if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
     const uint32_t parts = sort_parts(bound);
     const uint32_t parts_cap = sort_parts(a.capacity);
     for (uint32_t p = 0; p < num_passes; ++p) {
         uint32_t* lb = a.lookback + (size_t)p * parts_cap * SORT_BINS;
-        if (pib == 0)
-            onesweep_kernel<MODE_PAIRS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<true>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
-        else if (p == 0)
-            onesweep_kernel<MODE_PACK><<<parts, SORT_THREADS, sizeof(OnesweepSmem<false>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
+        if (words)
+            onesweep_kernel<MODE_WORDS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<false>), s>>>(a.keys[0], a.keys[1], nullptr, nullptr, a.ctl, a.plan, lb, p);
         else
-            onesweep_kernel<MODE_PACKED><<<parts, SORT_THREADS, sizeof(OnesweepSmem<false>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
+            onesweep_kernel<MODE_PAIRS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<true>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
     }
     return cudaGetLastError();
 }
 
-cudaError_t launch_sort_unpack(const SortLaunch& a, uint64_t* out_keys, uint32_t* out_vals, cudaStream_t s) {
-    sort_unpack_kernel<<<(uint32_t)a.sm_count * 8u, 256, 0, s>>>(a.keys[0], a.keys[1], a.plan, out_keys, out_vals);
+cudaError_t launch_sort_unpack(const RasterLaunch& a, uint64_t* out_keys, uint32_t* out_vals, int sm_count, cudaStream_t s) {
+    sort_unpack_kernel<<<(uint32_t)sm_count * 8u, 256, 0, s>>>(a, out_keys, out_vals);
     return cudaGetLastError();
 }
 

@@ -5,9 +5,11 @@
 // draw() -> read_frame / external-memory output. What differs by design:
 //   * no mid-frame GPU->CPU read-back of tilesRendered (GaussianEngine.cpp:662-674): P stays on the device,
 //     launches are sized by the grow-only pair capacity and an overflowing frame is re-rendered lazily;
-//   * 13 launches per frame (replayed from a CUDA graph) instead of 2 + 1 + 92 + 2 dispatches with 95 pipeline
+//   * a two-level sort: the visible Gaussians by depth, duplication in that order, then the pairs by tile only (sort.cu)
+//     instead of one 23-pass sort of every pair (GaussianEngine.cpp:822-841);
+//   * 17 launches per frame (replayed from a CUDA graph) instead of 2 + 1 + 92 + 2 dispatches with 95 pipeline
 //     barriers (GaussianEngine.cpp:777-863);
-//   * two frames in flight, like the reference's Frame objects (GaussianEngine.h:104-117, SurfaceRenderer.h:66): every
+//   * several frames in flight, like the reference's Frame objects (GaussianEngine.h:104-117, SurfaceRenderer.h:66): every
 //     frame slot owns its splat arrays, pair buffers and a private stream, so the memory-bound front of frame k+1
 //     (preprocess, sort) overlaps the SM-bound blend of frame k. Only the blend is ordered after the caller's stream
 //     (it is what writes the target); the caller's stream then waits for the frame.
@@ -40,13 +42,15 @@ static int fail(int code, const std::string& msg) {
         }                                                                                                         \
     } while (0)
 
+struct PlanHead {  // head of a SortPlan as the frame left it
+    uint32_t n, num_passes, final_sel, passes_run, bias, total_bits;
+};
+static_assert(offsetof(SortPlan, total_bits) == 5 * sizeof(uint32_t), "PlanHead mirrors the head of SortPlan");
 struct FrameStatus {  // pinned host mirror of what a frame reports back
     uint32_t pairs_total;
     uint32_t visible;
-    // head of the SortPlan as the frame left it
-    uint32_t n, num_passes, final_sel, passes_run, bias, depth_bits, total_bits, idx_bits, packed, packed_overflow;
+    PlanHead tile, depth;
 };
-static_assert(offsetof(SortPlan, packed_overflow) == 9 * sizeof(uint32_t), "FrameStatus mirrors the head of SortPlan");
 
 constexpr int MAX_SLOTS = 4;
 constexpr uint32_t TICKET_RING = 256;  // frames that may be enqueued between two host-side checks (tpdcu_finish & co.)
@@ -66,8 +70,7 @@ struct FrameTicket {
 
 struct GraphSig {  // everything a captured frame bakes in
     const void* zero_region; size_t zero_bytes; const void* keys0; const void* keys1; const void* geo; const void* posop;
-    uint32_t n, capacity, width, height, sh_degree, packed_idx_bits, packed_word_bits, entity_count;
-    uint32_t keep_unsorted;
+    uint32_t n, capacity, width, height, sh_degree, entity_count;
     bool operator==(const GraphSig& o) const { return memcmp(this, &o, sizeof(GraphSig)) == 0; }
 };
 
@@ -77,7 +80,9 @@ struct FrameSlot {
     SplatGeo* geo = nullptr;
     float4* color = nullptr;
     float2* depth_radius = nullptr;
+    uint2* rect = nullptr;
     uint32_t* offsets = nullptr;
+    uint64_t* depth_words[2] = { nullptr, nullptr };  // visible Gaussians: depth << 32 | index, ping-pong of the depth sort
     uint32_t n_alloc = 0;
     // camera-derived constants and model matrices
     FrameCam* cam = nullptr;
@@ -87,16 +92,15 @@ struct FrameSlot {
     uint32_t entity_alloc = 0;
     uint64_t models_version = 0;
     // sort / raster state
-    SortPlan* plan = nullptr;
+    SortPlan* plan = nullptr;        // tile sort (and the standalone pair sort)
+    SortPlan* depth_plan = nullptr;  // depth sort
     uint8_t* zero_region = nullptr;
-    size_t zero_bytes = 0, off_scan_desc = 0, off_ranges = 0, off_lookback = 0;
-    uint32_t zero_n = 0, zero_capacity = 0, zero_tiles = 0;
+    size_t zero_bytes = 0, off_scan_desc = 0, off_emit_desc = 0, off_ranges = 0, off_lb_depth = 0, off_lb_tile = 0;
+    uint32_t zero_n = 0, zero_capacity = 0, zero_tiles = 0, zero_tile_passes = 0;
     uint32_t capacity = 0;
-    uint64_t* keys[2] = { nullptr, nullptr };
-    uint32_t* vals[2] = { nullptr, nullptr };
-    uint64_t* unsorted_keys = nullptr;
-    uint32_t* unsorted_vals = nullptr;
-    uint32_t unsorted_capacity = 0;
+    uint64_t* keys[2] = { nullptr, nullptr };  // pair words tile << 32 | index, ping-pong of the tile sort
+    uint32_t* vals[2] = { nullptr, nullptr };  // standalone pair sort only
+    uint32_t vals_capacity = 0;
     // execution
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, done = nullptr;
@@ -127,9 +131,6 @@ struct tpdcu_ctx {
     int frames_in_flight = 3;
     int next_slot = 0;
 
-    uint32_t packed_word_bits = 64;
-    bool packed_disabled = false;  // a frame whose depth range did not fit packed sort words switches the context to pair mode
-    bool keep_unsorted = false;
     bool use_graph = true;
     uint32_t graph_launches = 0, graph_captures = 0;
     cudaStream_t capture_stream = nullptr;
@@ -148,7 +149,7 @@ struct tpdcu_ctx {
     uint32_t frames_repeated = 0;        // frames rendered again because they overflowed (grow-only buffers: warm-up only)
 
     bool timing = false;
-    cudaEvent_t ev[7] = {};
+    cudaEvent_t ev[9] = {};
     float stage_ms[TPDCU_NUM_STAGES] = {};
 
     // standalone sort
@@ -165,19 +166,11 @@ static uint32_t bit_length(uint32_t v) {
 static uint32_t tiles_of(const tpdcu_ctx* c) {
     return ((c->width + TILE_PX - 1) / TILE_PX) * ((c->height + TILE_PX - 1) / TILE_PX);
 }
-static uint32_t frame_end_bit(const tpdcu_ctx* c) {
+static uint32_t tile_bits_of(const tpdcu_ctx* c) {
     const uint32_t tiles = tiles_of(c);
-    return 32u + (tiles > 1 ? bit_length(tiles - 1) : 0u);
+    return tiles > 1 ? bit_length(tiles - 1) : 0u;
 }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-// Packed sort words hold tile | depth - bias | index (sort.cu). Used when the index and tile bits leave at least 24 bits for
-// the depth range of a frame (27 bits cover the default near/far planes); verified per frame on the device.
-static uint32_t packed_idx_bits(const tpdcu_ctx* c) {
-    if (c->packed_disabled || c->n == 0) return 0;
-    const uint32_t idx_bits = std::max(1u, bit_length(c->n - 1));
-    const uint32_t tile_bits = frame_end_bit(c) - 32u;
-    return (idx_bits + tile_bits <= 40u) ? idx_bits : 0u;
-}
 
 static void drop_graph(FrameSlot& f) {
     if (f.graph_exec) cudaGraphExecDestroy(f.graph_exec);
@@ -186,9 +179,11 @@ static void drop_graph(FrameSlot& f) {
 }
 
 static void free_slot_scene(FrameSlot& f) {
-    cudaFree(f.geo); cudaFree(f.color); cudaFree(f.depth_radius); cudaFree(f.offsets);
+    cudaFree(f.geo); cudaFree(f.color); cudaFree(f.depth_radius); cudaFree(f.rect); cudaFree(f.offsets);
+    cudaFree(f.depth_words[0]); cudaFree(f.depth_words[1]);
     cudaFree(f.models); cudaFree(f.vm); cudaFree(f.pm);
-    f.geo = nullptr; f.color = nullptr; f.depth_radius = nullptr; f.offsets = nullptr;
+    f.geo = nullptr; f.color = nullptr; f.depth_radius = nullptr; f.rect = nullptr; f.offsets = nullptr;
+    f.depth_words[0] = f.depth_words[1] = nullptr;
     f.models = f.vm = f.pm = nullptr;
     f.n_alloc = 0; f.entity_alloc = 0; f.models_version = 0;
     drop_graph(f);
@@ -197,6 +192,7 @@ static void free_slot_scene(FrameSlot& f) {
 static void free_slot_pairs(FrameSlot& f) {
     for (int i = 0; i < 2; ++i) { cudaFree(f.keys[i]); cudaFree(f.vals[i]); f.keys[i] = nullptr; f.vals[i] = nullptr; }
     f.capacity = 0;
+    f.vals_capacity = 0;
     drop_graph(f);
 }
 
@@ -213,6 +209,9 @@ static int ensure_slot_scene(tpdcu_ctx* c, FrameSlot& f) {
         CK(cudaMalloc(&f.geo, (size_t)c->n * sizeof(SplatGeo)));
         CK(cudaMalloc(&f.color, (size_t)c->n * sizeof(float4)));
         CK(cudaMalloc(&f.depth_radius, (size_t)c->n * sizeof(float2)));
+        CK(cudaMalloc(&f.rect, (size_t)c->n * sizeof(uint2)));
+        // whole sort tiles: the onesweep passes prefetch and pad by tile
+        for (int i = 0; i < 2; ++i) CK(cudaMalloc(&f.depth_words[i], align_up(c->n, SORT_TILE) * sizeof(uint64_t)));
         CK(cudaMalloc(&f.offsets, ((size_t)c->n + 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&f.models, (size_t)c->entity_count * 16 * sizeof(float)));
         CK(cudaMalloc(&f.vm, (size_t)c->entity_count * 16 * sizeof(float)));
@@ -230,30 +229,44 @@ static int ensure_pairs(FrameSlot& f, uint32_t want) {
     if (cap64 > 0xffffffffull - SORT_TILE) return fail(TPDCU_ERR_INVALID, "pair capacity exceeds 2^32");
     free_slot_pairs(f);
     const uint32_t cap = (uint32_t)cap64;
-    for (int i = 0; i < 2; ++i) {
-        CK(cudaMalloc(&f.keys[i], (size_t)cap * sizeof(uint64_t)));
-        CK(cudaMalloc(&f.vals[i], (size_t)cap * sizeof(uint32_t)));
-    }
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&f.keys[i], (size_t)cap * sizeof(uint64_t)));
     f.capacity = cap;
     return TPDCU_OK;
 }
 
-// The per-frame zeroed region: FrameCtl | scan descriptors | tile ranges | onesweep look-back arrays
-static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f) {
+static int ensure_vals(FrameSlot& f) {  // value buffers of the standalone pair sort
+    if (f.vals_capacity == f.capacity && f.vals[0]) return TPDCU_OK;
+    for (int i = 0; i < 2; ++i) { cudaFree(f.vals[i]); f.vals[i] = nullptr; }
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&f.vals[i], (size_t)f.capacity * sizeof(uint32_t)));
+    f.vals_capacity = f.capacity;
+    return TPDCU_OK;
+}
+
+// The per-frame zeroed region: FrameCtl | preprocess scan descriptors | duplication scan descriptors | tile ranges |
+// look-back arrays of the depth sort | look-back arrays of the tile sort (last: the standalone sort may need more passes)
+static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f, uint32_t tile_passes) {
     const uint32_t tiles = tiles_of(c);
-    if (f.zero_region && f.zero_n == c->n && f.zero_capacity == f.capacity && f.zero_tiles == tiles) return TPDCU_OK;
+    tile_passes = std::max(tile_passes, 1u);
+    if (f.zero_region && f.zero_n == c->n && f.zero_capacity == f.capacity && f.zero_tiles == tiles && f.zero_tile_passes >= tile_passes)
+        return TPDCU_OK;
     cudaFree(f.zero_region);
     f.zero_region = nullptr;
     drop_graph(f);
     const uint32_t pre_parts = (c->n + PRE_PART - 1) / PRE_PART;
     size_t off = align_up(sizeof(FrameCtl), 256);
     f.off_scan_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
+    f.off_emit_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
     f.off_ranges = off;    off = align_up(off + (size_t)tiles * 2 * sizeof(uint32_t), 256);
-    f.off_lookback = off;  off = align_up(off + (size_t)SORT_MAX_PASSES * sort_parts(f.capacity) * SORT_BINS * sizeof(uint32_t), 256);
+    f.off_lb_depth = off;  off = align_up(off + (size_t)sort_passes_for(32) * sort_parts(c->n) * SORT_BINS * sizeof(uint32_t), 256);
+    f.off_lb_tile = off;   off = align_up(off + (size_t)tile_passes * sort_parts(f.capacity) * SORT_BINS * sizeof(uint32_t), 256);
     CK(cudaMalloc(&f.zero_region, off));
     f.zero_bytes = off;
-    f.zero_n = c->n; f.zero_capacity = f.capacity; f.zero_tiles = tiles;
+    f.zero_n = c->n; f.zero_capacity = f.capacity; f.zero_tiles = tiles; f.zero_tile_passes = tile_passes;
     return TPDCU_OK;
+}
+// bytes of the zeroed region a sort with `tile_passes` passes over the pair buffers touches
+static size_t zero_bytes_for(const FrameSlot& f, uint32_t tile_passes) {
+    return std::min(f.zero_bytes, f.off_lb_tile + align_up((size_t)std::max(tile_passes, 1u) * sort_parts(f.capacity) * SORT_BINS * sizeof(uint32_t), 256));
 }
 
 static int ensure_status(tpdcu_ctx* c) {
@@ -281,37 +294,42 @@ static int sync_slots(tpdcu_ctx* c) {
 
 struct FrameLaunch {
     PreprocessLaunch pre;
-    SortLaunch sort;
+    SortLaunch depth_sort;
+    EmitLaunch emit;
+    SortLaunch tile_sort;
     RasterLaunch raster;
+    size_t zero_bytes;
 };
 
 // The part of a frame whose launch parameters do not change from frame to frame: everything between the camera setup and
 // the blend. Either enqueued directly or captured once into a CUDA graph and replayed.
 static int enqueue_middle(tpdcu_ctx* c, FrameSlot& f, const FrameLaunch& l, cudaStream_t s, bool timing) {
-    CK(cudaMemsetAsync(f.zero_region, 0, f.zero_bytes, s));
+    CK(cudaMemsetAsync(f.zero_region, 0, l.zero_bytes, s));
     if (timing) CK(cudaEventRecord(c->ev[1], s));
     CK(launch_preprocess(l.pre, s));
     CK(launch_color(l.pre, s));
-    if (c->keep_unsorted && f.capacity) {
-        CK(cudaMemcpyAsync(f.unsorted_keys, f.keys[0], (size_t)f.capacity * 8, cudaMemcpyDeviceToDevice, s));
-        CK(cudaMemcpyAsync(f.unsorted_vals, f.vals[0], (size_t)f.capacity * 4, cudaMemcpyDeviceToDevice, s));
-    }
     if (timing) CK(cudaEventRecord(c->ev[2], s));
-    CK(launch_sort(l.sort, UINT32_MAX, s, timing ? c->ev[3] : nullptr));
+    CK(launch_sort(l.depth_sort, 0, s, nullptr));
+    if (timing) CK(cudaEventRecord(c->ev[3], s));
+    CK(launch_emit(l.emit, s));
     if (timing) CK(cudaEventRecord(c->ev[4], s));
-    CK(launch_ranges(l.raster, s));
+    CK(launch_sort(l.tile_sort, 0, s, timing ? c->ev[8] : nullptr));
     if (timing) CK(cudaEventRecord(c->ev[5], s));
+    CK(launch_ranges(l.raster, f.capacity, s));
+    if (timing) CK(cudaEventRecord(c->ev[6], s));
     return TPDCU_OK;
 }
 
-// Enqueue the frame described by the ticket on slot `f`. No host synchronisation. With stage timing everything runs on the caller's stream; otherwise the front of the frame runs
-// on the slot's stream unordered with the caller's stream, the blend waits for the caller's stream (it writes the target)
-// and the caller's stream waits for the frame.
+// Enqueue the frame described by the ticket on slot `f`. No host synchronisation. With stage timing everything runs on the
+// caller's stream; otherwise the front of the frame runs on the slot's stream unordered with the caller's stream, the blend
+// waits for the caller's stream (it writes the target) and the caller's stream waits for the frame.
 static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     if (int r = ensure_slot_scene(c, f)) return r;
     if (f.capacity == 0)
         if (int r = ensure_pairs(f, SORT_TILE)) return r;
-    if (int r = ensure_zero_region(c, f)) return r;
+    const uint32_t tile_bits = tile_bits_of(c);
+    const uint32_t tile_passes = sort_passes_for(tile_bits);
+    if (int r = ensure_zero_region(c, f, tile_passes)) return r;
     const bool t = c->timing;
     cudaStream_t user = tk.user_stream;
     cudaStream_t s = t ? user : f.stream;
@@ -320,41 +338,42 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
         CK(cudaMemcpyAsync(f.models, c->models_host.data(), sizeof(float) * 16 * c->entity_count, cudaMemcpyHostToDevice, s));
         f.models_version = c->models_version;
     }
-    if (c->keep_unsorted && f.unsorted_capacity < f.capacity) {
-        cudaFree(f.unsorted_keys); cudaFree(f.unsorted_vals);
-        f.unsorted_keys = nullptr; f.unsorted_vals = nullptr; f.unsorted_capacity = 0;
-        drop_graph(f);
-        CK(cudaMalloc(&f.unsorted_keys, (size_t)f.capacity * 8));
-        CK(cudaMalloc(&f.unsorted_vals, (size_t)f.capacity * 4));
-        f.unsorted_capacity = f.capacity;
-    }
 
-    const uint32_t end_bit = frame_end_bit(c);
     FrameCtl* ctl = reinterpret_cast<FrameCtl*>(f.zero_region);
     FrameLaunch l{};
+    l.zero_bytes = zero_bytes_for(f, tile_passes);
     PreprocessLaunch& p = l.pre;
     p.scene = SceneArrays{ c->posop, c->cov_a, c->cov_b, c->sh, c->entity_count > 1 ? c->entity : nullptr, c->n, c->entity_count };
     p.models = f.models; p.cam = f.cam; p.vm = f.vm; p.pm = f.pm;
     p.ctl = ctl;
     p.scan_desc = reinterpret_cast<uint64_t*>(f.zero_region + f.off_scan_desc);
-    p.out = SplatArrays{ f.geo, f.color, f.depth_radius, f.offsets };
-    p.keys = f.keys[0]; p.vals = f.vals[0];
-    p.capacity = f.capacity;
+    p.out = SplatArrays{ f.geo, f.color, f.depth_radius, f.rect, f.offsets };
+    p.depth_words = f.depth_words[0];
     p.width = c->width; p.height = c->height; p.sh_degree = std::min(tk.sh_degree, 3u);  // GaussianEngine.cpp:366-370
 
-    SortLaunch& so = l.sort;
-    so.keys[0] = f.keys[0]; so.keys[1] = f.keys[1]; so.vals[0] = f.vals[0]; so.vals[1] = f.vals[1];
-    so.ctl = ctl; so.plan = f.plan;
-    so.lookback = reinterpret_cast<uint32_t*>(f.zero_region + f.off_lookback);
-    so.capacity = f.capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
-    so.packed_idx_bits = packed_idx_bits(c);
-    so.packed_word_bits = c->packed_word_bits;
+    SortLaunch& ds = l.depth_sort;
+    ds.keys[0] = f.depth_words[0]; ds.keys[1] = f.depth_words[1];
+    ds.frame = ctl; ds.ctl = &ctl->depth_sort; ds.plan = f.depth_plan;
+    ds.lookback = reinterpret_cast<uint32_t*>(f.zero_region + f.off_lb_depth);
+    ds.kind = SORT_KIND_DEPTH; ds.capacity = c->n; ds.end_bit = 32; ds.sm_count = c->sm_count;
+
+    EmitLaunch& em = l.emit;
+    em.depth_words[0] = f.depth_words[0]; em.depth_words[1] = f.depth_words[1];
+    em.depth_plan = f.depth_plan; em.rect = f.rect; em.ctl = ctl;
+    em.scan_desc = reinterpret_cast<uint64_t*>(f.zero_region + f.off_emit_desc);
+    em.keys = f.keys[0]; em.n = c->n; em.capacity = f.capacity; em.width = c->width;
+
+    SortLaunch& ts = l.tile_sort;
+    ts.keys[0] = f.keys[0]; ts.keys[1] = f.keys[1];
+    ts.frame = ctl; ts.ctl = &ctl->tile_sort; ts.plan = f.plan;
+    ts.lookback = reinterpret_cast<uint32_t*>(f.zero_region + f.off_lb_tile);
+    ts.kind = SORT_KIND_TILE; ts.capacity = f.capacity; ts.end_bit = tile_bits; ts.sm_count = c->sm_count;
 
     RasterLaunch& ra = l.raster;
-    ra.keys[0] = f.keys[0]; ra.keys[1] = f.keys[1]; ra.vals[0] = f.vals[0]; ra.vals[1] = f.vals[1];
-    ra.plan = f.plan; ra.geo = f.geo; ra.color = f.color;
+    ra.keys[0] = f.keys[0]; ra.keys[1] = f.keys[1];
+    ra.plan = f.plan; ra.geo = f.geo; ra.color = f.color; ra.depth_radius = f.depth_radius;
     ra.ranges = reinterpret_cast<uint32_t*>(f.zero_region + f.off_ranges);
-    ra.out = tk.out; ra.pitch = tk.pitch; ra.capacity = f.capacity; ra.width = c->width; ra.height = c->height;
+    ra.out = tk.out; ra.pitch = tk.pitch; ra.width = c->width; ra.height = c->height;
 
     if (t) CK(cudaEventRecord(c->ev[0], s));
     CameraUbo cu;
@@ -365,10 +384,9 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     if (c->use_graph && !t) {
         GraphSig sig;
         memset(&sig, 0, sizeof(sig));
-        sig.zero_region = f.zero_region; sig.zero_bytes = f.zero_bytes; sig.keys0 = f.keys[0]; sig.keys1 = f.keys[1];
+        sig.zero_region = f.zero_region; sig.zero_bytes = l.zero_bytes; sig.keys0 = f.keys[0]; sig.keys1 = f.keys[1];
         sig.geo = f.geo; sig.posop = c->posop; sig.n = c->n; sig.capacity = f.capacity; sig.width = c->width; sig.height = c->height;
-        sig.sh_degree = p.sh_degree; sig.packed_idx_bits = so.packed_idx_bits; sig.packed_word_bits = so.packed_word_bits;
-        sig.entity_count = c->entity_count; sig.keep_unsorted = c->keep_unsorted ? 1u : 0u;
+        sig.sh_degree = p.sh_degree; sig.entity_count = c->entity_count;
         if (!(f.graph_valid && f.graph_sig == sig)) {
             // (re)capture on a private stream: nothing executes during capture
             drop_graph(f);
@@ -405,11 +423,12 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
         CK(cudaStreamWaitEvent(s, f.fork, 0));
     }
     CK(launch_blend(ra, s));
-    if (t) CK(cudaEventRecord(c->ev[6], s));
+    if (t) CK(cudaEventRecord(c->ev[7], s));
 
     FrameStatus* st = &c->status[tk.status];
     CK(cudaMemcpyAsync(&st->pairs_total, &ctl->pairs_total, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&st->n, f.plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&st->tile, f.plan, sizeof(PlanHead), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&st->depth, f.depth_plan, sizeof(PlanHead), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(f.done, s));
     if (!t) CK(cudaStreamWaitEvent(user, f.done, 0));
     tk.ran_capacity = f.capacity;
@@ -469,7 +488,7 @@ static int raster_one(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cudaSt
 }
 
 // Host-side check of everything enqueued since the last check: wait for the frames, and render again (after growing the
-// buffers / leaving packed mode) those that overflowed — unless a later frame went to the same target, in which case the
+// buffers) those that overflowed — unless a later frame went to the same target, in which case the
 // frame has been superseded and repeating it would clobber the newer image.
 static int finish_internal(tpdcu_ctx* c) {
     if (!c->have_newest) return fail(TPDCU_ERR_STATE, "no frame has been rendered");
@@ -483,10 +502,8 @@ static int finish_internal(tpdcu_ctx* c) {
         for (size_t i = 0; i < pending.size(); ++i) {
             const FrameTicket& tk = pending[i];
             const FrameStatus& st = c->status[tk.status];
-            const bool overflow = st.pairs_total > tk.ran_capacity;
-            if (!overflow && !st.packed_overflow) continue;
-            if (overflow) max_pairs = std::max(max_pairs, st.pairs_total);
-            else c->packed_disabled = true;
+            if (st.pairs_total <= tk.ran_capacity) continue;
+            max_pairs = std::max(max_pairs, st.pairs_total);
             bool superseded = false;
             for (size_t j = i + 1; j < pending.size() && !superseded; ++j) superseded = pending[j].out == tk.out;
             if (!superseded) redo.push_back(tk);
@@ -503,13 +520,17 @@ static int finish_internal(tpdcu_ctx* c) {
     }
     if (int r = wait_slots(c)) return r;
     if (c->timing) {
-        CK(cudaEventSynchronize(c->ev[6]));
+        CK(cudaEventSynchronize(c->ev[7]));
         float ms;
-        // ev: 0 start | 1 after clear+setup | 2 after preprocess | 3 after hist+plan | 4 after passes | 5 after ranges | 6 after blend
-        for (int k = 0; k < 6; ++k) { CK(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1])); c->stage_ms[k] = ms; }
-        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[6]));
-        c->stage_ms[6] = ms;
-        c->stage_ms[7] = (float)c->status[c->newest.status].passes_run;
+        // ev: 0 start | 1 after clear+setup | 2 after preprocess+colour | 3 after the depth sort | 4 after duplication |
+        //     5 after the tile sort | 6 after ranges | 7 after blend
+        for (int k = 0; k < 7; ++k) { CK(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1])); c->stage_ms[k] = ms; }
+        CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[7]));
+        c->stage_ms[7] = ms;
+        c->stage_ms[8] = (float)c->status[c->newest.status].depth.passes_run;
+        c->stage_ms[9] = (float)c->status[c->newest.status].tile.passes_run;
+        CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[8]));
+        c->stage_ms[10] = ms;
     }
     return TPDCU_OK;
 }
@@ -558,6 +579,8 @@ int tpdcu_create(int device, tpdcu_ctx** out) {
         CKB(cudaMalloc(&f.cam, sizeof(FrameCam)));
         CKB(cudaMalloc(&f.plan, sizeof(SortPlan)));
         CKB(cudaMemset(f.plan, 0, sizeof(SortPlan)));
+        CKB(cudaMalloc(&f.depth_plan, sizeof(SortPlan)));
+        CKB(cudaMemset(f.depth_plan, 0, sizeof(SortPlan)));
         CKB(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
         CKB(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
         CKB(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
@@ -579,7 +602,7 @@ void tpdcu_destroy(tpdcu_ctx* c) {
     free_scene(c);
     for (auto& f : c->slots) {
         free_slot_pairs(f);
-        cudaFree(f.cam); cudaFree(f.plan); cudaFree(f.zero_region); cudaFree(f.unsorted_keys); cudaFree(f.unsorted_vals); cudaFree(f.target);
+        cudaFree(f.cam); cudaFree(f.plan); cudaFree(f.depth_plan); cudaFree(f.zero_region); cudaFree(f.target);
         if (f.stream) cudaStreamDestroy(f.stream);
         if (f.fork) cudaEventDestroy(f.fork);
         if (f.done) cudaEventDestroy(f.done);
@@ -801,7 +824,7 @@ int tpdcu_read_splats(tpdcu_ctx* c, void* host_splats48, uint32_t n) {
     FrameSlot& f = last(c);
     void* tmp = nullptr;
     CK(cudaMalloc(&tmp, (size_t)n * TPDCU_SPLAT_BYTES));
-    cudaError_t e = launch_export_splats(SplatArrays{ f.geo, f.color, f.depth_radius, f.offsets }, n, tmp, f.stream);
+    cudaError_t e = launch_export_splats(SplatArrays{ f.geo, f.color, f.depth_radius, f.rect, f.offsets }, n, tmp, f.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_splats48, tmp, (size_t)n * TPDCU_SPLAT_BYTES, cudaMemcpyDeviceToHost, f.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(f.stream);
     cudaFree(tmp);
@@ -817,21 +840,18 @@ static int read_sorted(tpdcu_ctx* c, void* host, uint32_t count, bool want_keys)
     FrameSlot& f = last(c);
     if (count > st.pairs_total) return fail(TPDCU_ERR_INVALID, "count exceeds the frame's pair count");
     if (count == 0) return TPDCU_OK;
-    const void* src;
-    if (st.packed) {
-        // the frame's result is one array of packed words: expand it into the reference's (key, value) arrays in the
-        // buffers the sort no longer needs
-        SortLaunch so{};
-        so.keys[0] = f.keys[0]; so.keys[1] = f.keys[1]; so.plan = f.plan; so.sm_count = c->sm_count;
-        uint64_t* uk = f.keys[(st.final_sel & 1u) ^ 1u];
-        uint32_t* uv = f.vals[1];
-        CK(launch_sort_unpack(so, uk, uv, f.stream));
-        src = want_keys ? (const void*)uk : (const void*)uv;
-    } else {
-        src = want_keys ? (const void*)f.keys[st.final_sel & 1u] : (const void*)f.vals[st.final_sel & 1u];
-    }
-    CK(cudaMemcpyAsync(host, src, (size_t)count * (want_keys ? 8 : 4), cudaMemcpyDeviceToHost, f.stream));
-    CK(cudaStreamSynchronize(f.stream));
+    // the frame's result is one array of words tile << 32 | index: expand it into the reference's (key, value) arrays
+    RasterLaunch ra{};
+    ra.keys[0] = f.keys[0]; ra.keys[1] = f.keys[1]; ra.plan = f.plan; ra.depth_radius = f.depth_radius;
+    uint64_t* uk = f.keys[(st.tile.final_sel & 1u) ^ 1u];  // the ping-pong buffer the sort no longer needs
+    uint32_t* uv = nullptr;
+    CK(cudaMalloc(&uv, (size_t)std::max(st.tile.n, 1u) * 4));
+    cudaError_t e = launch_sort_unpack(ra, uk, uv, c->sm_count, f.stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host, want_keys ? (const void*)uk : (const void*)uv, (size_t)count * (want_keys ? 8 : 4), cudaMemcpyDeviceToHost, f.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(f.stream);
+    cudaFree(uv);
+    if (e != cudaSuccess) return fail(TPDCU_ERR_CUDA, std::string("read_sorted: ") + cudaGetErrorString(e));
     return TPDCU_OK;
 }
 
@@ -848,21 +868,26 @@ int tpdcu_read_ranges(tpdcu_ctx* c, uint32_t* host_ranges2, uint32_t tile_count)
     return TPDCU_OK;
 }
 
-int tpdcu_keep_unsorted(tpdcu_ctx* c, int enable) {
-    if (int r = check_ready(c)) return r;
-    c->keep_unsorted = enable != 0;
-    return TPDCU_OK;
-}
-
 int tpdcu_read_unsorted(tpdcu_ctx* c, uint64_t* host_keys, uint32_t* host_vals, uint32_t count) {
     if (int r = check_ready(c)) return r;
     if (int r = finish_internal(c)) return r;
     FrameSlot& f = last(c);
-    if (!c->keep_unsorted || !f.unsorted_keys) return fail(TPDCU_ERR_STATE, "tpdcu_keep_unsorted was not enabled for the last frame");
-    if (count > last_status(c).pairs_total || count > f.unsorted_capacity) return fail(TPDCU_ERR_INVALID, "count exceeds the frame's pair count");
-    if (host_keys) CK(cudaMemcpyAsync(host_keys, f.unsorted_keys, (size_t)count * 8, cudaMemcpyDeviceToHost, f.stream));
-    if (host_vals) CK(cudaMemcpyAsync(host_vals, f.unsorted_vals, (size_t)count * 4, cudaMemcpyDeviceToHost, f.stream));
-    CK(cudaStreamSynchronize(f.stream));
+    if (count > last_status(c).pairs_total) return fail(TPDCU_ERR_INVALID, "count exceeds the frame's pair count");
+    if (count == 0) return TPDCU_OK;
+    // The frame itself never materialises the reference's unsorted buffers (its duplication runs in depth order): rebuild
+    // them from the per-Gaussian records, in the reference's order.
+    uint64_t* dk = nullptr;
+    uint32_t* dv = nullptr;
+    cudaError_t e = cudaMalloc(&dk, (size_t)count * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dv, (size_t)count * 4);
+    if (e == cudaSuccess)
+        e = launch_export_unsorted(SplatArrays{ f.geo, f.color, f.depth_radius, f.rect, f.offsets }, c->n, c->width, dk, dv, count, f.stream);
+    if (e == cudaSuccess && host_keys) e = cudaMemcpyAsync(host_keys, dk, (size_t)count * 8, cudaMemcpyDeviceToHost, f.stream);
+    if (e == cudaSuccess && host_vals) e = cudaMemcpyAsync(host_vals, dv, (size_t)count * 4, cudaMemcpyDeviceToHost, f.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(f.stream);
+    cudaFree(dk);
+    cudaFree(dv);
+    if (e != cudaSuccess) return fail(TPDCU_ERR_CUDA, std::string("read_unsorted: ") + cudaGetErrorString(e));
     return TPDCU_OK;
 }
 
@@ -879,26 +904,20 @@ int tpdcu_stage_times_ms(tpdcu_ctx* c, float times_ms[TPDCU_NUM_STAGES]) {
     if (!times_ms) return fail(TPDCU_ERR_INVALID, "times_ms is null");
     if (!c->timing) return fail(TPDCU_ERR_STATE, "stage timing is not enabled");
     if (int r = finish_internal(c)) return r;
-    // stage_ms[k] = ev[k+1]-ev[k]: 0 clear+setup | 1 preprocess | 2 hist+plan | 3 passes | 4 ranges | 5 blend
+    // 0 clear+setup | 1 preprocess+colour | 2 depth sort | 3 duplication | 4 tile sort | 5 ranges | 6 blend | 7 frame |
+    // 8 depth-sort passes run | 9 tile-sort passes run | 10 histogram+plan share of the tile sort
     memcpy(times_ms, c->stage_ms, sizeof(float) * TPDCU_NUM_STAGES);
     return TPDCU_OK;
 }
 
-int tpdcu_get_sort_info(tpdcu_ctx* c, uint32_t* packed, uint32_t* depth_bits, uint32_t* idx_bits, uint32_t* total_bits) {
+int tpdcu_get_sort_info(tpdcu_ctx* c, uint32_t* depth_bits, uint32_t* depth_passes, uint32_t* tile_bits, uint32_t* tile_passes) {
     if (int r = check_ready(c)) return r;
     if (int r = finish_internal(c)) return r;
     const FrameStatus& st = last_status(c);
-    if (packed) *packed = st.packed;
-    if (depth_bits) *depth_bits = st.depth_bits;
-    if (idx_bits) *idx_bits = st.idx_bits;
-    if (total_bits) *total_bits = st.total_bits;
-    return TPDCU_OK;
-}
-
-int tpdcu_set_packed_word_bits(tpdcu_ctx* c, uint32_t bits) {
-    if (int r = check_ready(c)) return r;
-    if (bits < 1 || bits > 64) return fail(TPDCU_ERR_INVALID, "bits must be in [1, 64]");
-    c->packed_word_bits = bits;
+    if (depth_bits) *depth_bits = st.depth.total_bits;
+    if (depth_passes) *depth_passes = st.depth.passes_run;
+    if (tile_bits) *tile_bits = st.tile.total_bits;
+    if (tile_passes) *tile_passes = st.tile.passes_run;
     return TPDCU_OK;
 }
 
@@ -959,22 +978,25 @@ int tpdcu_sort_pairs_device(tpdcu_ctx* c, uint64_t* d_keys, uint32_t* d_vals, ui
     }
     if (f.capacity == 0)
         if (int r = ensure_pairs(f, SORT_TILE)) return r;
-    if (int r = ensure_zero_region(c, f)) return r;
-    CK(cudaMemsetAsync(f.zero_region, 0, f.zero_bytes, s));
+    if (int r = ensure_vals(f)) return r;
+    const uint32_t passes = sort_passes_for(end_bit);
+    if (int r = ensure_zero_region(c, f, passes)) return r;
+    CK(cudaMemsetAsync(f.zero_region, 0, zero_bytes_for(f, passes), s));
     if (n) {
         CK(cudaMemcpyAsync(f.keys[0], d_keys, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(f.vals[0], d_vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
     }
+    FrameCtl* ctl = reinterpret_cast<FrameCtl*>(f.zero_region);
     SortLaunch so{};
     so.keys[0] = f.keys[0]; so.keys[1] = f.keys[1]; so.vals[0] = f.vals[0]; so.vals[1] = f.vals[1];
-    so.ctl = reinterpret_cast<FrameCtl*>(f.zero_region); so.plan = f.plan;
-    so.lookback = reinterpret_cast<uint32_t*>(f.zero_region + f.off_lookback);
-    so.capacity = f.capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
+    so.frame = ctl; so.ctl = &ctl->tile_sort; so.plan = f.plan;
+    so.lookback = reinterpret_cast<uint32_t*>(f.zero_region + f.off_lb_tile);
+    so.kind = SORT_KIND_PAIRS; so.capacity = f.capacity; so.end_bit = end_bit; so.sm_count = c->sm_count;
     CK(cudaEventRecord(c->sort_ev[0], s));
     CK(launch_sort(so, n, s, nullptr));
     CK(cudaEventRecord(c->sort_ev[1], s));
     CK(launch_sort_copy_result(so, d_keys, d_vals, n, s));
-    CK(cudaMemcpyAsync(&c->status[TICKET_RING - 1].n, f.plan, 10 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&c->status[TICKET_RING - 1].tile, f.plan, sizeof(PlanHead), cudaMemcpyDeviceToHost, s));
     c->sort_stream = s;
     c->sort_done = true;
     return TPDCU_OK;
@@ -988,7 +1010,7 @@ int tpdcu_sort_last_ms(tpdcu_ctx* c, float* ms, uint32_t* passes_run) {
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, c->sort_ev[0], c->sort_ev[1]));
     if (ms) *ms = t;
-    if (passes_run) *passes_run = c->status[TICKET_RING - 1].passes_run;
+    if (passes_run) *passes_run = c->status[TICKET_RING - 1].tile.passes_run;
     return TPDCU_OK;
 }
 

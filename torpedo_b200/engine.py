@@ -303,25 +303,20 @@ class GaussianEngine:
         check(tpdcu().tpdcu_read_ranges(self._ctx, _ptr(out), tiles))
         return out
 
-    def keep_unsorted(self, enable: bool = True) -> None:
-        check(tpdcu().tpdcu_keep_unsorted(self._ctx, int(enable)))
-
     def enable_stage_timing(self, enable: bool = True) -> None:
         check(tpdcu().tpdcu_enable_stage_timing(self._ctx, int(enable)))
 
     def stage_times_ms(self) -> dict:
         t = np.zeros(_lib.NUM_STAGES, dtype=np.float32)
         check(tpdcu().tpdcu_stage_times_ms(self._ctx, _ptr(t)))
-        names = ["setup", "preprocess", "sort_hist", "sort_passes", "ranges", "blend", "frame", "passes_run"]
+        names = ["setup", "preprocess", "depth_sort", "duplicate", "tile_sort", "ranges", "blend", "frame",
+                 "depth_passes_run", "tile_passes_run", "tile_sort_hist_plan"]
         return dict(zip(names, [float(x) for x in t]))
 
     def sort_info(self) -> dict:
-        p, d, i, t = u32(0), u32(0), u32(0), u32(0)
-        check(tpdcu().tpdcu_get_sort_info(self._ctx, C.byref(p), C.byref(d), C.byref(i), C.byref(t)))
-        return {"packed": bool(p.value), "depth_bits": d.value, "idx_bits": i.value, "total_bits": t.value}
-
-    def set_packed_word_bits(self, bits: int) -> None:
-        check(tpdcu().tpdcu_set_packed_word_bits(self._ctx, bits))
+        d, dp, t, tp = u32(0), u32(0), u32(0), u32(0)
+        check(tpdcu().tpdcu_get_sort_info(self._ctx, C.byref(d), C.byref(dp), C.byref(t), C.byref(tp)))
+        return {"depth_bits": d.value, "depth_passes": dp.value, "tile_bits": t.value, "tile_passes": tp.value}
 
     def graph_replay(self, enable: int = -1) -> tuple[int, int]:
         """Switch CUDA-graph replay of the frame on (1) / off (0) or just query (-1); returns (captures, launches)."""
