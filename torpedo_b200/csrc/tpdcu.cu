@@ -103,7 +103,8 @@ struct FrameSlot {
     uint32_t vals_capacity = 0;
     // execution
     cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, done = nullptr;
+    cudaEvent_t fork = nullptr, done = nullptr, read_done = nullptr;
+    bool read_pending = false;  // an asynchronous read of `target` has been enqueued since the slot last rendered into it
     bool graph_valid = false;
     GraphSig graph_sig;
     cudaGraphExec_t graph_exec = nullptr;
@@ -418,9 +419,16 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     if (!replayed)
         if (int r = enqueue_middle(c, f, l, s, t)) return r;
 
-    if (!t) {  // the blend writes the caller's target: order it after whatever the caller's stream did with that memory
-        CK(cudaEventRecord(f.fork, user));
-        CK(cudaStreamWaitEvent(s, f.fork, 0));
+    if (!t) {
+        if (tk.out == f.target) {
+            // the slot's own target: the only other user is an asynchronous read of the frame it held before
+            // (tpdcu_read_frame_async); the blend does not have to wait for the newer frames' copies on the caller's stream
+            if (f.read_pending) CK(cudaStreamWaitEvent(s, f.read_done, 0));
+            f.read_pending = false;
+        } else {  // the blend writes the caller's memory: order it after whatever the caller's stream did with it
+            CK(cudaEventRecord(f.fork, user));
+            CK(cudaStreamWaitEvent(s, f.fork, 0));
+        }
     }
     CK(launch_blend(ra, s));
     if (t) CK(cudaEventRecord(c->ev[7], s));
@@ -584,6 +592,7 @@ int tpdcu_create(int device, tpdcu_ctx** out) {
         CKB(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
         CKB(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
         CKB(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+        CKB(cudaEventCreateWithFlags(&f.read_done, cudaEventDisableTiming));
     }
     CKB(cudaStreamCreateWithFlags(&c->capture_stream, cudaStreamNonBlocking));
     for (auto& e : c->ev) CKB(cudaEventCreate(&e));
@@ -606,6 +615,7 @@ void tpdcu_destroy(tpdcu_ctx* c) {
         if (f.stream) cudaStreamDestroy(f.stream);
         if (f.fork) cudaEventDestroy(f.fork);
         if (f.done) cudaEventDestroy(f.done);
+        if (f.read_done) cudaEventDestroy(f.read_done);
     }
     if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
     if (c->ext_mem) cudaDestroyExternalMemory(c->ext_mem);
@@ -797,6 +807,11 @@ int tpdcu_read_frame_async(tpdcu_ctx* c, void* host_rgba8, size_t host_pitch_byt
     // `stream` must be the stream the frame was rastered with (it already waits for the frame); no host synchronisation here
     CK(cudaMemcpy2DAsync(host_rgba8, host_pitch_bytes, c->newest.out, c->newest.pitch, (size_t)c->width * 4, c->height,
                          cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    FrameSlot& f = last(c);
+    if (c->newest.out == f.target) {  // the next frame of this slot must not overwrite the target before the copy has read it
+        CK(cudaEventRecord(f.read_done, (cudaStream_t)stream));
+        f.read_pending = true;
+    }
     return TPDCU_OK;
 }
 
