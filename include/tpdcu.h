@@ -131,9 +131,10 @@ int tpdcu_read_unsorted(tpdcu_ctx* ctx, uint64_t* host_keys, uint32_t* host_vals
  * [8] / [9] number of onesweep passes the depth sort / the tile sort actually ran [10] histogram+plan share of [4]. */
 int tpdcu_enable_stage_timing(tpdcu_ctx* ctx, int enable);
 int tpdcu_stage_times_ms(tpdcu_ctx* ctx, float times_ms[TPDCU_NUM_STAGES]);
-/* How the last finished frame was sorted (two levels, see csrc/sort.cu): the visible Gaussians by the `depth_bits` bits the
- * frame's depth range occupies (words depth << 32 | index, 16 B moved per Gaussian and pass), then the pairs by their
- * `tile_bits` tile bits (words tile << 32 | index, 16 B per pair and pass); *_passes = onesweep passes that ran. */
+/* How the last finished frame was sorted (two levels, see csrc/sort.cu): the visible Gaussians by `depth_bits` low bits of
+ * (depth - frame minimum) (words depth << 32 | index, 16 B moved per Gaussian and pass), then the pairs by `tile_bits` bits:
+ * the tile id above whatever top depth bits did not fill a whole 8-bit digit of the depth sort (words key << 32 | index,
+ * 16 B per pair and pass); *_passes = onesweep passes that ran. */
 int tpdcu_get_sort_info(tpdcu_ctx* ctx, uint32_t* depth_bits, uint32_t* depth_passes, uint32_t* tile_bits, uint32_t* tile_passes);
 /* The frame's launches between the camera setup and the blend do not change from frame to frame; they are captured once
  * into a CUDA graph and replayed (the reference re-records two command buffers every frame, GaussianEngine.cpp:637-697).

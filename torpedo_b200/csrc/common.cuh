@@ -46,10 +46,21 @@ struct FrameCtl {
 
 // Which sort a launch performs: where n and the key geometry come from.
 //   SORT_KIND_PAIRS  standalone API: (u64 key, u32 value) pairs, bits [0, end_bit), n from the host
-//   SORT_KIND_DEPTH  words  float_bits(viewZ) << 32 | Gaussian index, n = FrameCtl::visible, sorted on (depth - frame
-//                    minimum): only the bits the frame's depth range occupies are sorted (26 at 1080p with default planes)
-//   SORT_KIND_TILE   words  tile << 32 | Gaussian index, n = min(FrameCtl::pairs_total, capacity), end_bit tile bits
+//   SORT_KIND_DEPTH  words  float_bits(viewZ) << 32 | Gaussian index, n = FrameCtl::visible, sorted on the LOW bits of
+//                    (depth - frame minimum), see DepthSplit
+//   SORT_KIND_TILE   words  (tile << extra | top depth bits) << 32 | Gaussian index, n = min(FrameCtl::pairs_total, capacity)
 enum : uint32_t { SORT_KIND_PAIRS = 0, SORT_KIND_DEPTH = 1, SORT_KIND_TILE = 2 };
+
+// How a frame's sort key  tile | depth - minimum  is cut between the two sorts. Only the bits the frame's depth range
+// occupies matter (26 at 1080p with the default planes). Both sorts work in 8-bit digits: when the depth bits leave a
+// partial digit (26 = 3 x 8 + 2) and the tile sort has room in its last digit (13 tile bits use 2 x 8), those top depth bits
+// ride below the tile id in the pair key and the depth sort drops a whole pass.
+struct DepthSplit {
+    uint32_t bias;        // frame minimum of float_bits(viewZ)
+    uint32_t low_bits;    // bits of (depth - bias) sorted by the depth sort
+    uint32_t extra;       // top bits of (depth - bias) carried in the pair key, below the tile id
+};
+__device__ __forceinline__ DepthSplit depth_split(const FrameCtl* fr, uint32_t tile_bits);
 
 // Written by the plan kernel, read by every sort pass and by the consumers of the sorted result.
 struct SortPlan {
@@ -59,7 +70,8 @@ struct SortPlan {
     uint32_t passes_run;
     uint32_t bias;                        // words: subtracted from the key (high 32 bits) before digit extraction
     uint32_t total_bits;                  // key bits the passes sort on
-    uint32_t pad[2];
+    uint32_t tile_shift;                  // tile sort: DepthSplit::extra, the tile id sits above that many depth bits
+    uint32_t pad;
     uint32_t skip[SORT_MAX_PASSES];       // pass is an identity permutation (single occupied bin)
     uint32_t src_sel[SORT_MAX_PASSES];    // ping-pong buffer the pass reads from
 };
@@ -121,6 +133,18 @@ __device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ DepthSplit depth_split(const FrameCtl* fr, uint32_t tile_bits) {
+    const uint32_t dmin = ~fr->inv_depth_min, dmax = fr->depth_max;
+    DepthSplit x;
+    x.bias = dmax >= dmin ? dmin : 0u;
+    const uint32_t depth_bits = dmax >= dmin ? 32u - __clz(dmax - dmin) : 0u;  // 0 when every Gaussian carries the same depth
+    const uint32_t rem = depth_bits % SORT_RADIX_BITS;
+    const uint32_t spare = (tile_bits + SORT_RADIX_BITS - 1) / SORT_RADIX_BITS * SORT_RADIX_BITS - tile_bits;
+    x.extra = (rem != 0 && rem <= spare) ? rem : 0u;
+    x.low_bits = depth_bits - x.extra;
+    return x;
+}
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
@@ -165,10 +189,11 @@ struct EmitLaunch {
     const uint2* rect;
     FrameCtl* ctl;
     uint64_t* scan_desc;                  // zeroed, one per partition
-    uint64_t* keys;                       // out: tile << 32 | index
+    uint64_t* keys;                       // out: (tile << extra | top depth bits) << 32 | index
     uint32_t n;                           // scene size (launch bound)
     uint32_t capacity;
     uint32_t width;
+    uint32_t tile_bits;
 };
 cudaError_t launch_emit(const EmitLaunch& a, cudaStream_t s);
 
@@ -185,7 +210,8 @@ struct SortLaunch {
     uint32_t* lookback;                   // zeroed, [num_passes][parts_cap][SORT_BINS]
     uint32_t kind;
     uint32_t capacity;                    // launch bound for grids
-    uint32_t end_bit;                     // pairs: end bit of the key; depth: 32; tile: tile bits
+    uint32_t end_bit;                     // pairs: end bit of the key; depth: 32; tile: tile bits rounded up to whole digits
+    uint32_t tile_bits;                   // depth / tile: bits of the largest tile id (DepthSplit)
     int sm_count;
 };
 // n_host is used by SORT_KIND_PAIRS only.

@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
     __shared__ uint64_t s_base;
     __shared__ uint32_t s_off[EMIT_PART];       // exclusive pair offsets inside the partition
     __shared__ uint32_t s_xy[EMIT_PART];        // rect origin: x0 | y0 << 16
-    __shared__ uint32_t s_w[EMIT_PART];         // rect width
+    __shared__ uint32_t s_w[EMIT_PART];         // rect width | top depth bits << 16 (DepthSplit::extra of them)
     __shared__ uint32_t s_id[EMIT_PART];        // Gaussian index
     __shared__ uint32_t s_warp_tot[EMIT_ITEMS][EMIT_THREADS / 32];
 
@@ -446,6 +446,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
     if ((uint64_t)part * EMIT_PART >= visible) return;
     const uint64_t* __restrict__ sorted = a.depth_plan->final_sel ? a.depth_words[1] : a.depth_words[0];
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX;
+    const DepthSplit ds = depth_split(a.ctl, a.tile_bits);
 
     // ---- gather: blocked, so that a thread's EMIT_ITEMS Gaussians are consecutive in depth order -----------------------
     uint32_t cnt[EMIT_ITEMS];
@@ -453,15 +454,17 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
     for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
         const uint32_t slot = k * EMIT_THREADS + tid;           // striped loads (coalesced), partition order = slot order
         const uint32_t r = part * EMIT_PART + slot;
-        uint32_t id = 0;
+        uint32_t id = 0, dtop = 0;
         uint2 rc = make_uint2(0u, 0u);
         if (r < visible) {
-            id = (uint32_t)__ldg(sorted + r);
+            const uint64_t word = __ldg(sorted + r);
+            id = (uint32_t)word;
+            if (ds.extra) dtop = ((uint32_t)(word >> 32) - ds.bias) >> ds.low_bits;
             rc = __ldg(a.rect + id);
         }
         cnt[k] = (rc.y & 0xffffu) * (rc.y >> 16);
         s_xy[slot] = rc.x;
-        s_w[slot] = rc.y & 0xffffu;
+        s_w[slot] = (rc.y & 0xffffu) | (dtop << 16);
         s_id[slot] = id;
     }
 
@@ -519,7 +522,8 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
 #pragma unroll
         for (uint32_t step = EMIT_PART / 2; step >= 1; step >>= 1)
             if (s_off[g + step] <= j) g += step;
-        uint32_t w = s_w[g], xy = s_xy[g], id = s_id[g];
+        uint32_t wd = s_w[g], xy = s_xy[g], id = s_id[g];
+        uint32_t w = wd & 0xffffu;
         const uint32_t r = j - s_off[g];
         const uint32_t ry = r / w;
         uint32_t rx = r - ry * w;
@@ -537,7 +541,8 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
                             ++g;
                             next_off = g + 1 < EMIT_PART ? s_off[g + 1] : 0xffffffffu;
                         } while (jq >= next_off);
-                        w = s_w[g]; xy = s_xy[g]; id = s_id[g];
+                        wd = s_w[g]; xy = s_xy[g]; id = s_id[g];
+                        w = wd & 0xffffu;
                         rx = 0;
                         row = (xy >> 16) * gx + (xy & 0xffffu);
                     } else if (++rx == w) {
@@ -545,7 +550,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
                         row += gx;
                     }
                 }
-                key[q] = ((uint64_t)(row + rx) << 32) | id;
+                key[q] = ((uint64_t)(((row + rx) << ds.extra) | (wd >> 16)) << 32) | id;
             }
         }
         if (lo == G0 && hi == G0 + 4u && G0 + 4u <= a.capacity) {

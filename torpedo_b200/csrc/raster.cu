@@ -15,7 +15,7 @@ namespace tpdcu {
 __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
     const uint32_t n = a.plan->n;
     const uint64_t* __restrict__ keys = a.plan->final_sel ? a.keys[1] : a.keys[0];
-    constexpr uint32_t tshift = 32u;  // words are tile << 32 | Gaussian index
+    const uint32_t tshift = 32u + a.plan->tile_shift;  // words are (tile << shift | top depth bits) << 32 | Gaussian index
     uint2* ranges = reinterpret_cast<uint2*>(a.ranges);
     // two keys per thread with one 16-byte load; the key before the pair comes from the neighbour's line (L1 hit)
     const uint32_t pairs2 = (n + 1) / 2;

@@ -33,17 +33,18 @@ constexpr uint32_t SORT_PREFETCH_TILES = TPDCU_SORT_PREFETCH_TILES;  // 148 SMs 
 struct SortSpec {
     uint32_t n, bias, total_bits;
 };
-__device__ __forceinline__ SortSpec sort_spec(const FrameCtl* fr, uint32_t kind, uint32_t n_host, uint32_t capacity, uint32_t end_bit) {
+__device__ __forceinline__ SortSpec sort_spec(const FrameCtl* fr, uint32_t kind, uint32_t n_host, uint32_t capacity, uint32_t end_bit,
+                                              uint32_t tile_bits) {
     SortSpec x;
     if (kind == SORT_KIND_PAIRS) {
         x.n = n_host; x.bias = 0; x.total_bits = end_bit;
-    } else if (kind == SORT_KIND_DEPTH) {
-        const uint32_t dmin = ~fr->inv_depth_min, dmax = fr->depth_max;
-        x.n = min(fr->visible, capacity);
-        x.bias = dmax >= dmin ? dmin : 0u;
-        x.total_bits = dmax >= dmin ? 32u - __clz(dmax - dmin) : 0u;  // 0 when every Gaussian carries the same depth
     } else {
-        x.n = min(fr->pairs_total, capacity); x.bias = 0; x.total_bits = end_bit;
+        const DepthSplit ds = depth_split(fr, tile_bits);
+        if (kind == SORT_KIND_DEPTH) {
+            x.n = min(fr->visible, capacity); x.bias = ds.bias; x.total_bits = ds.low_bits;
+        } else {
+            x.n = min(fr->pairs_total, capacity); x.bias = 0; x.total_bits = tile_bits + ds.extra;
+        }
     }
     return x;
 }
@@ -65,9 +66,10 @@ __host__ __device__ __forceinline__ uint32_t passes_needed(uint32_t total_bits) 
 
 template <bool WORDS>
 __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t* __restrict__ keys, const FrameCtl* frame, SortCtl* ctl,
-                                                                  uint32_t kind, uint32_t n_host, uint32_t capacity, uint32_t end_bit) {
+                                                                  uint32_t kind, uint32_t n_host, uint32_t capacity, uint32_t end_bit,
+                                                                  uint32_t tile_bits) {
     __shared__ uint32_t h[SORT_MAX_PASSES][SORT_BINS];
-    const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit);
+    const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit, tile_bits);
     const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
     for (uint32_t k = threadIdx.x; k < num_passes * SORT_BINS; k += HIST_THREADS) (&h[0][0])[k] = 0;
     __syncthreads();
@@ -124,10 +126,10 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
 // ---------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(const FrameCtl* frame, SortCtl* ctl, SortPlan* plan, uint32_t kind,
-                                                               uint32_t n_host, uint32_t capacity, uint32_t end_bit) {
+                                                               uint32_t n_host, uint32_t capacity, uint32_t end_bit, uint32_t tile_bits) {
     __shared__ uint32_t s_warp[SORT_BINS / 32];
     __shared__ uint32_t s_skip[SORT_MAX_PASSES];
-    const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit);
+    const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit, tile_bits);
     const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
     const uint32_t b = threadIdx.x, lane = b & 31u, warp = b >> 5;
     if (b < SORT_MAX_PASSES) s_skip[b] = 0;
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(const FrameCtl* fr
         plan->passes_run = run;
         plan->bias = sp.bias;
         plan->total_bits = sp.total_bits;
+        plan->tile_shift = kind == SORT_KIND_TILE ? depth_split(frame, tile_bits).extra : 0u;
     }
 }
 
@@ -382,7 +385,7 @@ __global__ void sort_unpack_kernel(RasterLaunch a, uint64_t* out_keys, uint32_t*
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint64_t x = w[i];
         const uint32_t g = (uint32_t)x;
-        out_keys[i] = (x & 0xffffffff00000000ull) | __float_as_uint(a.depth_radius[g].x);
+        out_keys[i] = ((x >> (32u + a.plan->tile_shift)) << 32) | __float_as_uint(a.depth_radius[g].x);
         out_vals[i] = g;
     }
 }
@@ -419,7 +422,7 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     const uint32_t num_passes = passes_needed(a.end_bit);  // upper bound; the plan kernel marks the passes a frame does not need
     const uint32_t bound = words ? a.capacity : n_host;
     if (bound == 0 || num_passes == 0) {
-        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.frame, a.ctl, a.plan, bound == 0 ? (uint32_t)SORT_KIND_PAIRS : a.kind, 0u, a.capacity, 0u);
+        sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.frame, a.ctl, a.plan, bound == 0 ? (uint32_t)SORT_KIND_PAIRS : a.kind, 0u, a.capacity, 0u, a.tile_bits);
         if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
         return cudaGetLastError();
     }
@@ -427,9 +430,9 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     uint32_t hist_grid = (bound + chunk - 1) / chunk;
     const uint32_t hist_max = (uint32_t)a.sm_count * 4u;
     if (hist_grid > hist_max) hist_grid = hist_max;
-    if (words) sort_hist_kernel<true><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.kind, n_host, a.capacity, a.end_bit);
-    else sort_hist_kernel<false><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.kind, n_host, a.capacity, a.end_bit);
-    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit);
+    if (words) sort_hist_kernel<true><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
+    else sort_hist_kernel<false><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
+    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
     if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
     const uint32_t parts = sort_parts(bound);
     const uint32_t parts_cap = sort_parts(a.capacity);

@@ -356,19 +356,20 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     ds.keys[0] = f.depth_words[0]; ds.keys[1] = f.depth_words[1];
     ds.frame = ctl; ds.ctl = &ctl->depth_sort; ds.plan = f.depth_plan;
     ds.lookback = reinterpret_cast<uint32_t*>(f.zero_region + f.off_lb_depth);
-    ds.kind = SORT_KIND_DEPTH; ds.capacity = c->n; ds.end_bit = 32; ds.sm_count = c->sm_count;
+    ds.kind = SORT_KIND_DEPTH; ds.capacity = c->n; ds.end_bit = 32; ds.tile_bits = tile_bits; ds.sm_count = c->sm_count;
 
     EmitLaunch& em = l.emit;
     em.depth_words[0] = f.depth_words[0]; em.depth_words[1] = f.depth_words[1];
     em.depth_plan = f.depth_plan; em.rect = f.rect; em.ctl = ctl;
     em.scan_desc = reinterpret_cast<uint64_t*>(f.zero_region + f.off_emit_desc);
-    em.keys = f.keys[0]; em.n = c->n; em.capacity = f.capacity; em.width = c->width;
+    em.keys = f.keys[0]; em.n = c->n; em.capacity = f.capacity; em.width = c->width; em.tile_bits = tile_bits;
 
     SortLaunch& ts = l.tile_sort;
     ts.keys[0] = f.keys[0]; ts.keys[1] = f.keys[1];
     ts.frame = ctl; ts.ctl = &ctl->tile_sort; ts.plan = f.plan;
     ts.lookback = reinterpret_cast<uint32_t*>(f.zero_region + f.off_lb_tile);
-    ts.kind = SORT_KIND_TILE; ts.capacity = f.capacity; ts.end_bit = tile_bits; ts.sm_count = c->sm_count;
+    // whole digits: the top depth bits that do not fill a digit of the depth sort ride in the pair key (DepthSplit)
+    ts.kind = SORT_KIND_TILE; ts.capacity = f.capacity; ts.end_bit = tile_passes * SORT_RADIX_BITS; ts.tile_bits = tile_bits; ts.sm_count = c->sm_count;
 
     RasterLaunch& ra = l.raster;
     ra.keys[0] = f.keys[0]; ra.keys[1] = f.keys[1];
