@@ -10,7 +10,7 @@ constexpr uint32_t TILE_PX = 16;          // BLOCK_X == BLOCK_Y (reference Gauss
 constexpr uint32_t PRE_THREADS = 256;
 constexpr uint32_t PRE_ITEMS = 4;         // Gaussians per thread
 constexpr uint32_t PRE_PART = PRE_THREADS * PRE_ITEMS;  // Gaussians per preprocess partition (one look-back each)
-constexpr uint32_t SH_PLANES = 12;        // 48 SH floats as 12 float4 planes
+constexpr uint32_t SH_PLANES = 12;        // 48 SH floats = 12 float4 per Gaussian
 constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
@@ -105,7 +105,7 @@ struct SceneArrays {
     const float4* posop;                  // xyz + opacity
     const float4* cov_a;                  // S00 S01 S02 S11
     const float2* cov_b;                  // S12 S22
-    const float4* sh;                     // [SH_PLANES][n], float index f = 3*coef + channel
+    const float4* sh;                     // [n][SH_PLANES]: one 192-byte row per Gaussian, float index f = 3*coef + channel
     const uint32_t* entity;               // nullptr when the scene has a single entity
     uint32_t n;
     uint32_t entity_count;

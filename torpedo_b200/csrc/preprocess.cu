@@ -53,9 +53,9 @@ __global__ void __launch_bounds__(COMPILE_THREADS) compile_scene_kernel(CompileL
     a.cov_a[i] = make_float4(cov(0, 0), cov(0, 1), cov(0, 2), cov(1, 1));
     a.cov_b[i] = make_float2(cov(1, 2), cov(2, 2));
 
-    // SH: reference layout is DC rgb then 15 R, 15 G, 15 B (splat/common.slang:25-31);
-    // internal layout is coefficient-major rgb triplets so that degree d touches the first
-    // ceil(3*(d+1)^2/4) planes only.
+    // SH: reference layout is DC rgb then 15 R, 15 G, 15 B (splat/common.slang:25-31); internal layout is one 192-byte
+    // row per Gaussian of coefficient-major rgb triplets, so that degree d touches the first ceil(3*(d+1)^2/4) float4 of
+    // the row only and a row is fetched with whole 32-byte sectors whatever its neighbours' visibility.
     const float* sh = g + 12;
 #pragma unroll
     for (uint32_t p = 0; p < SH_PLANES; ++p) {
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(COMPILE_THREADS) compile_scene_kernel(CompileL
             const uint32_t f = p * 4 + q, k = f / 3, c = f % 3;
             v[q] = (k == 0) ? sh[c] : sh[3 + c * 15 + (k - 1)];
         }
-        a.sh[(size_t)p * a.n + i] = make_float4(v[0], v[1], v[2], v[3]);
+        a.sh[(size_t)i * SH_PLANES + p] = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -574,29 +574,59 @@ cudaError_t launch_emit(const EmitLaunch& a, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// colour: SH evaluation for the visible Gaussians only (project.slang:82-83, splat/common.slang:35-80). No barriers, no
-// look-back: a pure stream of 16 B position + up to 192 B of SH in, 16 B out, runs after the geometry kernel.
+// colour: SH evaluation for the visible Gaussians only (project.slang:82-83, splat/common.slang:35-80). No look-back, no
+// block barrier: a pure stream of 16 B position + up to 192 B of SH in, 16 B out, DRAM-bound. Every visible Gaussian's SH
+// row is pulled into shared memory by ONE bulk-copy (TMA) instruction issued by its own thread — exact 32-byte sectors, no
+// bytes fetched for culled neighbours, and the load instructions of a 48-float gather disappear.
 // ---------------------------------------------------------------------------------------------------
 
-constexpr uint32_t COLOR_THREADS = 256;
+constexpr uint32_t COLOR_THREADS = 128;
+constexpr uint32_t COLOR_ROW_F4 = SH_PLANES + 1;  // odd stride in 16-byte units: the per-thread 128-bit row reads are conflict-free
 
 template <int DEG>
 __global__ void __launch_bounds__(COLOR_THREADS) color_kernel(PreprocessLaunch a) {
-    const uint32_t n = a.scene.n;
-    const uint32_t i = blockIdx.x * COLOR_THREADS + threadIdx.x;
-    if (i >= n) return;
-    if (a.out.offsets[i + 1] == a.out.offsets[i]) return;  // culled: the reference leaves its colour stale
-    const float4 po = __ldg(a.scene.posop + i);
-    float shf[48];
     constexpr int PLANES = DEG == 0 ? 1 : DEG == 1 ? 3 : DEG == 2 ? 7 : 12;
+    __shared__ __align__(128) float4 rows[COLOR_THREADS * COLOR_ROW_F4];
+    __shared__ __align__(8) uint64_t mbar[COLOR_THREADS / 32];
+    const uint32_t n = a.scene.n;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t i = blockIdx.x * COLOR_THREADS + tid;
+    const bool vis = i < n && a.out.offsets[i + 1] != a.out.offsets[i];  // culled: the reference leaves its colour stale
+    const uint32_t vmask = __ballot_sync(0xffffffffu, vis);
+    if (vmask == 0) return;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[warp]);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)__popc(vmask) * (uint32_t)(PLANES * 16)) : "memory");
+    float4* row = rows + tid * COLOR_ROW_F4;
+    if (vis)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(row)),
+                     "l"(a.scene.sh + (size_t)i * SH_PLANES), "r"((uint32_t)(PLANES * 16)), "r"(bar)
+                     : "memory");
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (vis) {
+        const float4 po = __ldg(a.scene.posop + i);
+        dx = po.x - a.cam->cam_pos[0]; dy = po.y - a.cam->cam_pos[1]; dz = po.z - a.cam->cam_pos[2];
+        const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
+        dx /= len; dy /= len; dz /= len;
+    }
+    {
+        uint32_t ready = 0;
+        while (!ready)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ready) : "r"(bar) : "memory");
+    }
+    if (!vis) return;
+    float shf[48];
 #pragma unroll
     for (int p = 0; p < PLANES; ++p) {
-        const float4 v = __ldg(a.scene.sh + (size_t)p * n + i);
+        const float4 v = row[p];
         shf[4 * p + 0] = v.x; shf[4 * p + 1] = v.y; shf[4 * p + 2] = v.z; shf[4 * p + 3] = v.w;
     }
-    float dx = po.x - a.cam->cam_pos[0], dy = po.y - a.cam->cam_pos[1], dz = po.z - a.cam->cam_pos[2];
-    const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
-    dx /= len; dy /= len; dz /= len;
     const float3 col = eval_sh(shf, dx, dy, dz, DEG);
     a.out.color[i] = make_float4(col.x, col.y, col.z, 0.0f);
 }
