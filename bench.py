@@ -294,7 +294,7 @@ def run_gpu(args):
     hosts_np = [hbuf.numpy() for hbuf in hosts]
     copied = [torch.cuda.Event() for _ in range(NBUF)]
     cam = E.PerspectiveCamera(WIDTH, HEIGHT)
-    e2e_steps = min(K, 24)
+    e2e_steps = min(K, 64)
     for s in range(3):
         cam.look_at(E.to_cartesian(*ring_camera_params(s * world + rank)), (0, 0, 0), (0, 0, 1))
         eng.raster_frame(cam, stream)

@@ -15,10 +15,10 @@ constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
 #ifndef TPDCU_SORT_KPT
-#define TPDCU_SORT_KPT 16
+#define TPDCU_SORT_KPT 24
 #endif
 #ifndef TPDCU_SORT_MINB
-#define TPDCU_SORT_MINB 3
+#define TPDCU_SORT_MINB 2
 #endif
 constexpr uint32_t SORT_THREADS = 256;
 constexpr uint32_t SORT_KPT = TPDCU_SORT_KPT;  // keys per thread
