@@ -321,11 +321,12 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         // keeps busy (ncu: ADU 39 %, LSU 57 % with match.any) — the ballot form made every pass ~20 % faster.
         uint32_t peers = 0xffffffffu;
 #pragma unroll
-        for (uint32_t bit = 0; bit < SORT_RADIX_BITS; ++bit) {
-            const bool set = (d >> bit) & 1u;
-            const uint32_t b = __ballot_sync(0xffffffffu, set);
-            peers &= set ? b : ~b;
-        }
+        for (uint32_t bit = 0; bit < SORT_RADIX_BITS; ++bit)
+            asm("{\n\t.reg .pred p;\n\t.reg .b32 b;\n\t"
+                "and.b32 b, %1, %2;\n\tsetp.ne.u32 p, b, 0;\n\t"
+                "vote.sync.ballot.b32 b, p, 0xffffffff;\n\t"
+                "@!p not.b32 b, b;\n\tand.b32 %0, %0, b;\n\t}"
+                : "+r"(peers) : "r"(d), "r"(1u << bit));
         const uint32_t lower = __popc(peers & lanemask_lt());
         const uint32_t base = sm.warp_hist[warp][d];
         __syncwarp();
