@@ -15,14 +15,19 @@ constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
 #ifndef TPDCU_SORT_KPT
-#define TPDCU_SORT_KPT 24
+#define TPDCU_SORT_KPT 32
 #endif
 #ifndef TPDCU_SORT_MINB
 #define TPDCU_SORT_MINB 2
 #endif
 constexpr uint32_t SORT_THREADS = 256;
-constexpr uint32_t SORT_KPT = TPDCU_SORT_KPT;  // keys per thread
-constexpr uint32_t SORT_TILE = SORT_THREADS * SORT_KPT;
+// keys per thread: 32 for the single-word sorts of a frame (8192-key tiles, two CTAs per SM: fewer look-backs and more
+// independent work per thread beat occupancy), 16 for the standalone (key, value) pair sort, whose values double the state
+constexpr uint32_t SORT_KPT_WORDS = TPDCU_SORT_KPT;
+constexpr uint32_t SORT_KPT_PAIRS = 16;
+constexpr uint32_t SORT_TILE_WORDS = SORT_THREADS * SORT_KPT_WORDS;
+constexpr uint32_t SORT_TILE_PAIRS = SORT_THREADS * SORT_KPT_PAIRS;
+constexpr uint32_t SORT_TILE = SORT_TILE_WORDS > SORT_TILE_PAIRS ? SORT_TILE_WORDS : SORT_TILE_PAIRS;  // buffer granularity
 constexpr uint32_t SORT_WARPS = SORT_THREADS / 32;
 
 // Tickets and digit histograms of one radix sort.
@@ -216,7 +221,7 @@ struct SortLaunch {
 };
 // n_host is used by SORT_KIND_PAIRS only.
 cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cudaEvent_t ev_after_plan);
-uint32_t sort_parts(uint32_t capacity);
+uint32_t sort_parts(uint32_t capacity, uint32_t kind);
 uint32_t sort_passes_for(uint32_t end_bit);
 cudaError_t init_sort_attributes();
 

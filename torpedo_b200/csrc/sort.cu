@@ -28,7 +28,7 @@ constexpr uint32_t LOOKBACK_BATCH = TPDCU_LOOKBACK_BATCH;
 #define TPDCU_SORT_PREFETCH_TILES 296
 #endif
 #ifndef TPDCU_SORT_MINB_WORDS
-#define TPDCU_SORT_MINB_WORDS 3
+#define TPDCU_SORT_MINB_WORDS 2
 #endif
 constexpr uint32_t SORT_PREFETCH_TILES = TPDCU_SORT_PREFETCH_TILES;  // 148 SMs x 3 resident CTAs
 
@@ -180,18 +180,20 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(const FrameCtl* fr
 // scatter through shared memory disappears.
 enum : int { MODE_PAIRS = 0, MODE_WORDS = 1 };
 
-template <bool WITH_VALS>
+template <int MODE>
 struct OnesweepSmem {
-    uint64_t keys[SORT_TILE];
+    static constexpr bool WITH_VALS = MODE == MODE_PAIRS;
+    static constexpr uint32_t TILE = MODE == MODE_PAIRS ? SORT_TILE_PAIRS : SORT_TILE_WORDS;
+    uint64_t keys[TILE];
     alignas(16) uint32_t warp_hist[SORT_WARPS][SORT_BINS];  // zeroed with 16-byte stores
     uint32_t global_base[SORT_BINS];
     uint32_t scan[SORT_BINS / 32];
     uint32_t part;
-    uint32_t vals[WITH_VALS ? SORT_TILE : 1];
+    uint32_t vals[WITH_VALS ? TILE : 1];
 };
 static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phases");
 
-// One CTA = one tile of SORT_TILE pairs. Phases (block barriers in between):
+// One CTA = one tile of TILE elements. Phases (block barriers in between):
 //   ticket + zero per-warp histograms | load keys, early counts | per-bin: warp prefix, publish aggregate, bin scan |
 //   stable ranking (ballots) + scatter to smem | look-back per bin | coalesced write-out (+ value scatter / write-out)
 template <int MODE>
@@ -199,7 +201,9 @@ __global__ void __launch_bounds__(SORT_THREADS, MODE == MODE_WORDS ? TPDCU_SORT_
 onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, SortCtl* ctl,
                 const SortPlan* __restrict__ plan, uint32_t* lookback_pass, uint32_t pass) {
     constexpr bool IN_PAIRS = MODE == MODE_PAIRS, OUT_PAIRS = MODE == MODE_PAIRS, WORDS = MODE == MODE_WORDS;
-    using Smem = OnesweepSmem<OUT_PAIRS>;
+    using Smem = OnesweepSmem<MODE>;
+    constexpr uint32_t SORT_KPT = MODE == MODE_PAIRS ? SORT_KPT_PAIRS : SORT_KPT_WORDS;  // shadows nothing: per-mode tile shape
+    constexpr uint32_t SORT_TILE = Smem::TILE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -414,13 +418,16 @@ __global__ void sort_copy_result_kernel(const uint64_t* keys1, const uint32_t* v
     }
 }
 
-uint32_t sort_parts(uint32_t capacity) { return (capacity + SORT_TILE - 1) / SORT_TILE; }
+uint32_t sort_parts(uint32_t capacity, uint32_t kind) {
+    const uint32_t tile = kind == SORT_KIND_PAIRS ? SORT_TILE_PAIRS : SORT_TILE_WORDS;
+    return (capacity + tile - 1) / tile;
+}
 uint32_t sort_passes_for(uint32_t end_bit) { return passes_needed(end_bit); }
 
 template <int MODE>
 static cudaError_t set_smem_attr() {
     return cudaFuncSetAttribute(onesweep_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(OnesweepSmem<MODE == MODE_PAIRS>));
+                                (int)sizeof(OnesweepSmem<MODE>));
 }
 
 // opt in to > 48 KB of dynamic shared memory; called once per context, outside any stream capture
@@ -447,14 +454,14 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     else sort_hist_kernel<false><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
     sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
     if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
-    const uint32_t parts = sort_parts(bound);
-    const uint32_t parts_cap = sort_parts(a.capacity);
+    const uint32_t parts = sort_parts(bound, a.kind);
+    const uint32_t parts_cap = sort_parts(a.capacity, a.kind);
     for (uint32_t p = 0; p < num_passes; ++p) {
         uint32_t* lb = a.lookback + (size_t)p * parts_cap * SORT_BINS;
         if (words)
-            onesweep_kernel<MODE_WORDS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<false>), s>>>(a.keys[0], a.keys[1], nullptr, nullptr, a.ctl, a.plan, lb, p);
+            onesweep_kernel<MODE_WORDS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<MODE_WORDS>), s>>>(a.keys[0], a.keys[1], nullptr, nullptr, a.ctl, a.plan, lb, p);
         else
-            onesweep_kernel<MODE_PAIRS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<true>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
+            onesweep_kernel<MODE_PAIRS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<MODE_PAIRS>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
     }
     return cudaGetLastError();
 }

@@ -96,7 +96,8 @@ struct FrameSlot {
     SortPlan* depth_plan = nullptr;  // depth sort
     uint8_t* zero_region = nullptr;
     size_t zero_bytes = 0, off_scan_desc = 0, off_emit_desc = 0, off_ranges = 0, off_lb_depth = 0, off_lb_tile = 0;
-    uint32_t zero_n = 0, zero_capacity = 0, zero_tiles = 0, zero_tile_passes = 0;
+    uint32_t zero_n = 0, zero_capacity = 0, zero_tiles = 0;
+    size_t zero_lb_tile_bytes = 0;
     uint32_t capacity = 0;
     uint64_t* keys[2] = { nullptr, nullptr };  // pair words tile << 32 | index, ping-pong of the tile sort
     uint32_t* vals[2] = { nullptr, nullptr };  // standalone pair sort only
@@ -245,11 +246,14 @@ static int ensure_vals(FrameSlot& f) {  // value buffers of the standalone pair 
 
 // The per-frame zeroed region: FrameCtl | preprocess scan descriptors | duplication scan descriptors | tile ranges |
 // look-back arrays of the depth sort | look-back arrays of the tile sort (last: the standalone sort may need more passes)
-static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f, uint32_t tile_passes) {
+static size_t lookback_bytes(const FrameSlot& f, uint32_t passes, uint32_t kind) {
+    return align_up((size_t)std::max(passes, 1u) * sort_parts(f.capacity, kind) * SORT_BINS * sizeof(uint32_t), 256);
+}
+static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f, size_t lb_tile_bytes) {
     const uint32_t tiles = tiles_of(c);
-    tile_passes = std::max(tile_passes, 1u);
-    if (f.zero_region && f.zero_n == c->n && f.zero_capacity == f.capacity && f.zero_tiles == tiles && f.zero_tile_passes >= tile_passes)
+    if (f.zero_region && f.zero_n == c->n && f.zero_capacity == f.capacity && f.zero_tiles == tiles && f.zero_lb_tile_bytes >= lb_tile_bytes)
         return TPDCU_OK;
+    lb_tile_bytes = std::max(lb_tile_bytes, f.zero_capacity == f.capacity ? f.zero_lb_tile_bytes : (size_t)0);
     cudaFree(f.zero_region);
     f.zero_region = nullptr;
     drop_graph(f);
@@ -258,17 +262,15 @@ static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f, uint32_t tile_passes) 
     f.off_scan_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
     f.off_emit_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
     f.off_ranges = off;    off = align_up(off + (size_t)tiles * 2 * sizeof(uint32_t), 256);
-    f.off_lb_depth = off;  off = align_up(off + (size_t)sort_passes_for(32) * sort_parts(c->n) * SORT_BINS * sizeof(uint32_t), 256);
-    f.off_lb_tile = off;   off = align_up(off + (size_t)tile_passes * sort_parts(f.capacity) * SORT_BINS * sizeof(uint32_t), 256);
+    f.off_lb_depth = off;  off = align_up(off + (size_t)sort_passes_for(32) * sort_parts(c->n, SORT_KIND_DEPTH) * SORT_BINS * sizeof(uint32_t), 256);
+    f.off_lb_tile = off;   off += lb_tile_bytes;
     CK(cudaMalloc(&f.zero_region, off));
     f.zero_bytes = off;
-    f.zero_n = c->n; f.zero_capacity = f.capacity; f.zero_tiles = tiles; f.zero_tile_passes = tile_passes;
+    f.zero_n = c->n; f.zero_capacity = f.capacity; f.zero_tiles = tiles; f.zero_lb_tile_bytes = lb_tile_bytes;
     return TPDCU_OK;
 }
-// bytes of the zeroed region a sort with `tile_passes` passes over the pair buffers touches
-static size_t zero_bytes_for(const FrameSlot& f, uint32_t tile_passes) {
-    return std::min(f.zero_bytes, f.off_lb_tile + align_up((size_t)std::max(tile_passes, 1u) * sort_parts(f.capacity) * SORT_BINS * sizeof(uint32_t), 256));
-}
+// bytes of the zeroed region a launch whose pair-buffer look-back arrays take `lb_tile_bytes` touches
+static size_t zero_bytes_for(const FrameSlot& f, size_t lb_tile_bytes) { return std::min(f.zero_bytes, f.off_lb_tile + lb_tile_bytes); }
 
 static int ensure_status(tpdcu_ctx* c) {
     if (c->status) return TPDCU_OK;
@@ -330,7 +332,8 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
         if (int r = ensure_pairs(f, SORT_TILE)) return r;
     const uint32_t tile_bits = tile_bits_of(c);
     const uint32_t tile_passes = sort_passes_for(tile_bits);
-    if (int r = ensure_zero_region(c, f, tile_passes)) return r;
+    const size_t lb_tile_bytes = lookback_bytes(f, tile_passes, SORT_KIND_TILE);
+    if (int r = ensure_zero_region(c, f, lb_tile_bytes)) return r;
     const bool t = c->timing;
     cudaStream_t user = tk.user_stream;
     cudaStream_t s = t ? user : f.stream;
@@ -342,7 +345,7 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
 
     FrameCtl* ctl = reinterpret_cast<FrameCtl*>(f.zero_region);
     FrameLaunch l{};
-    l.zero_bytes = zero_bytes_for(f, tile_passes);
+    l.zero_bytes = zero_bytes_for(f, lb_tile_bytes);
     PreprocessLaunch& p = l.pre;
     p.scene = SceneArrays{ c->posop, c->cov_a, c->cov_b, c->sh, c->entity_count > 1 ? c->entity : nullptr, c->n, c->entity_count };
     p.models = f.models; p.cam = f.cam; p.vm = f.vm; p.pm = f.pm;
@@ -995,9 +998,9 @@ int tpdcu_sort_pairs_device(tpdcu_ctx* c, uint64_t* d_keys, uint32_t* d_vals, ui
     if (f.capacity == 0)
         if (int r = ensure_pairs(f, SORT_TILE)) return r;
     if (int r = ensure_vals(f)) return r;
-    const uint32_t passes = sort_passes_for(end_bit);
-    if (int r = ensure_zero_region(c, f, passes)) return r;
-    CK(cudaMemsetAsync(f.zero_region, 0, zero_bytes_for(f, passes), s));
+    const size_t lb_bytes = lookback_bytes(f, sort_passes_for(end_bit), SORT_KIND_PAIRS);
+    if (int r = ensure_zero_region(c, f, lb_bytes)) return r;
+    CK(cudaMemsetAsync(f.zero_region, 0, zero_bytes_for(f, lb_bytes), s));
     if (n) {
         CK(cudaMemcpyAsync(f.keys[0], d_keys, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(f.vals[0], d_vals, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
