@@ -3,12 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one frame of the hot path (preprocess+scan+duplication -> onesweep sort -> ranges -> blend). At N > 1
+A "step" is one frame of the hot path (preprocess+scan -> depth sort of the visible Gaussians -> duplication -> tile sort of
+the pairs -> ranges -> blend). At N > 1
 (launched under torchrun, one rank per GPU) the Gaussian set is replicated with one NCCL broadcast, independent camera
 views are sharded round-robin across ranks (view = step * N + rank) and the finished frames are gathered on rank 0 with
 NCCL inside the timed region — weak scaling; `value` = max-over-ranks time / total frames.
 
-JSON keys beyond the base contract: `roofline` (the onesweep pass kernel against measured HBM peak), `cpu_baseline`
+JSON keys beyond the base contract: `roofline` (the onesweep pass kernel of the tile sort against measured HBM peak), `cpu_baseline`
 (the CPU oracle on the host cores), `e2e` (camera on the host -> rasterFrame -> draw() into pinned host memory),
 `stages_ms`, `sort_gkeys_per_s`, `pairs`, `visible`, `clocks`.
 
