@@ -8,7 +8,11 @@ namespace tpdcu {
 
 constexpr uint32_t TILE_PX = 16;          // BLOCK_X == BLOCK_Y (reference GaussianEngine.h:122-123)
 constexpr uint32_t PRE_THREADS = 256;
-constexpr uint32_t PRE_ITEMS = 4;         // Gaussians per thread
+#ifndef TPDCU_PRE_ITEMS
+#define TPDCU_PRE_ITEMS 4
+#endif
+constexpr uint32_t PRE_ITEMS = TPDCU_PRE_ITEMS;  // Gaussians per thread
+constexpr uint32_t PRE_BATCH = 4;         // of which this many are in flight at a time
 constexpr uint32_t PRE_PART = PRE_THREADS * PRE_ITEMS;  // Gaussians per preprocess partition (one look-back each)
 constexpr uint32_t SH_PLANES = 12;        // 48 SH floats = 12 float4 per Gaussian
 constexpr uint32_t SORT_RADIX_BITS = 8;
@@ -201,6 +205,7 @@ struct EmitLaunch {
     uint32_t tile_bits;
 };
 cudaError_t launch_emit(const EmitLaunch& a, cudaStream_t s);
+uint32_t emit_parts(uint32_t n);  // duplication partitions (one scan descriptor each)
 
 // introspection: the reference's unsorted (key, value) buffers, in the reference's (index) order
 cudaError_t launch_export_unsorted(const SplatArrays& a, uint32_t n, uint32_t width, uint64_t* keys, uint32_t* vals, uint32_t capacity,

@@ -303,32 +303,37 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
     const uint32_t first = part * PRE_PART + tid;
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX, gy = (a.height + TILE_PX - 1) / TILE_PX;
 
-    // ---- geometry: all loads first, then the arithmetic ---------------------------------------------------------------
-    float4 po[PRE_ITEMS], ca[PRE_ITEMS];
-    float2 cb[PRE_ITEMS];
-#pragma unroll
-    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
-        const uint32_t i = first + k * PRE_THREADS;
-        if (i < n) {
-            po[k] = __ldg(a.scene.posop + i);
-            ca[k] = __ldg(a.scene.cov_a + i);
-            cb[k] = __ldg(a.scene.cov_b + i);
-        }
-    }
+    // ---- geometry, in batches of PRE_BATCH Gaussians per thread: all loads of a batch first, then its arithmetic. Only the
+    // tile count and the depth bits of a Gaussian stay in registers (project_one stores the records), so a partition can
+    // hold several batches: fewer partitions = fewer look-backs and less waiting on them per Gaussian.
     Projected pr[PRE_ITEMS];
 #pragma unroll
-    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
-        const uint32_t i = first + k * PRE_THREADS;
-        pr[k] = Projected{ 0u, 0u };
-        if (i < n) {
-            if (single_entity) {
-                pr[k] = project_one(a, i, po[k], ca[k], cb[k], s_vm, s_pm, s_v, s_focal, gx, gy);
-            } else {
-                float vm_l[16], pm_l[16];
-                const uint32_t e = __ldg(a.scene.entity + i);
+    for (uint32_t b0 = 0; b0 < PRE_ITEMS; b0 += PRE_BATCH) {
+        float4 po[PRE_BATCH], ca[PRE_BATCH];
+        float2 cb[PRE_BATCH];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) { vm_l[q] = __ldg(a.vm + e * 16 + q); pm_l[q] = __ldg(a.pm + e * 16 + q); }
-                pr[k] = project_one(a, i, po[k], ca[k], cb[k], vm_l, pm_l, s_v, s_focal, gx, gy);
+        for (uint32_t k = 0; k < PRE_BATCH; ++k) {
+            const uint32_t i = first + (b0 + k) * PRE_THREADS;
+            if (i < n) {
+                po[k] = __ldg(a.scene.posop + i);
+                ca[k] = __ldg(a.scene.cov_a + i);
+                cb[k] = __ldg(a.scene.cov_b + i);
+            }
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < PRE_BATCH; ++k) {
+            const uint32_t i = first + (b0 + k) * PRE_THREADS;
+            pr[b0 + k] = Projected{ 0u, 0u };
+            if (i < n) {
+                if (single_entity) {
+                    pr[b0 + k] = project_one(a, i, po[k], ca[k], cb[k], s_vm, s_pm, s_v, s_focal, gx, gy);
+                } else {
+                    float vm_l[16], pm_l[16];
+                    const uint32_t e = __ldg(a.scene.entity + i);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) { vm_l[q] = __ldg(a.vm + e * 16 + q); pm_l[q] = __ldg(a.pm + e * 16 + q); }
+                    pr[b0 + k] = project_one(a, i, po[k], ca[k], cb[k], vm_l, pm_l, s_v, s_focal, gx, gy);
+                }
             }
         }
     }
@@ -567,9 +572,11 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
     }
 }
 
+uint32_t emit_parts(uint32_t n) { return (n + EMIT_PART - 1) / EMIT_PART; }
+
 cudaError_t launch_emit(const EmitLaunch& a, cudaStream_t s) {
     if (a.n == 0) return cudaSuccess;
-    emit_kernel<<<(a.n + EMIT_PART - 1) / EMIT_PART, EMIT_THREADS, 0, s>>>(a);
+    emit_kernel<<<emit_parts(a.n), EMIT_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -260,7 +260,7 @@ static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f, size_t lb_tile_bytes) 
     const uint32_t pre_parts = (c->n + PRE_PART - 1) / PRE_PART;
     size_t off = align_up(sizeof(FrameCtl), 256);
     f.off_scan_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
-    f.off_emit_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
+    f.off_emit_desc = off; off = align_up(off + (size_t)emit_parts(c->n) * sizeof(uint64_t), 256);
     f.off_ranges = off;    off = align_up(off + (size_t)tiles * 2 * sizeof(uint32_t), 256);
     f.off_lb_depth = off;  off = align_up(off + (size_t)sort_passes_for(32) * sort_parts(c->n, SORT_KIND_DEPTH) * SORT_BINS * sizeof(uint32_t), 256);
     f.off_lb_tile = off;   off += lb_tile_bytes;
