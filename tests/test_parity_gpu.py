@@ -265,6 +265,43 @@ def test_two_level_sort_info_and_equal_depths(E, oracle):
     eng.close()
 
 
+def test_depth_split_corner_cases(E, oracle):
+    """The cut of tile | depth between the two sorts (DepthSplit, csrc/common.cuh): every Gaussian at the SAME depth (zero
+    depth bits: the depth sort has nothing to do), and a tile grid whose id fills whole digits (no room for depth bits)."""
+    from torpedo_b200 import scenes
+    _, cams = golden_cameras()
+    g = scenes.garden(3000, seed=5, log_scale_mean=-3.2)
+    g[:, 0:3] = g[0, 0:3]  # one position, 3000 different shapes / colours / opacities
+    for (w, h, cam) in [(256, 144, "garden_256x144")]:
+        ref = oracle.render(g, cams[cam], w, h, 3)
+        scene = E.Scene()
+        scene.add_group(g)
+        eng = E.GaussianEngine(w, h)
+        eng.compile(scene)
+        eng.raster_ubo(cams[cam], 3)
+        img = eng.draw()
+        info = eng.sort_info()
+        assert info["depth_bits"] == 0 and info["depth_passes"] == 0
+        if ref.pairs:
+            assert_frame_parity(eng, img, ref, len(g))
+        eng.close()
+    # 16 x 16 tiles = exactly 8 tile bits: top depth bits cannot ride in the pair key, the depth sort takes them all
+    g = scenes.garden(20000, seed=9, log_scale_mean=-3.6)
+    cam = E.PerspectiveCamera(256, 256)
+    cam.look_at((2.8, 2.8, 2.6), (0, 0, 0), (0, 0, 1))
+    ref = oracle.render(g, cam.pack(), 256, 256, 2)
+    scene = E.Scene()
+    scene.add_group(g)
+    eng = E.GaussianEngine(256, 256)
+    eng.compile(scene, E.Settings(2))
+    eng.raster_frame(cam)
+    img = eng.draw()
+    info = eng.sort_info()
+    assert info["tile_bits"] == 8 and info["tile_passes"] == 1 and info["depth_passes"] == (info["depth_bits"] + 7) // 8
+    assert_frame_parity(eng, img, ref, len(g))
+    eng.close()
+
+
 def test_cpp_hello_gaussian_demo(E, oracle, built_libs):
     """The reference's HelloGaussian demo compiled against the header-only C++ drop-in gives the same frame as the oracle."""
     import os
