@@ -154,6 +154,24 @@ __device__ __forceinline__ DepthSplit depth_split(const FrameCtl* fr, uint32_t t
     return x;
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.ENL2.256): a thread that owns 32 contiguous bytes moves a whole sector with one
+// instruction instead of two half-sector ones. `p` must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const uint64_t* p, uint64_t (&v)[4]) {
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(uint64_t* p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float4* p, const float4& a, const float4& b) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+                 "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;

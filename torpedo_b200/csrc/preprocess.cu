@@ -272,9 +272,8 @@ __device__ __forceinline__ Projected project_one(const PreprocessLaunch& a, uint
         ext_x = sqrtf(tt * cvx) * 1.0002f + 0.02f;
         ext_y = sqrtf(tt * cvz) * 1.0002f + 0.02f;
     }
-    float4* geo = reinterpret_cast<float4*>(a.out.geo + i);
-    geo[0] = make_float4(px, py, cvz * det_inv, -cvy * det_inv);
-    geo[1] = make_float4(cvx * det_inv, po.w, ext_x, ext_y);
+    stg256(reinterpret_cast<float4*>(a.out.geo + i), make_float4(px, py, cvz * det_inv, -cvy * det_inv),
+           make_float4(cvx * det_inv, po.w, ext_x, ext_y));  // the 32-byte SplatGeo record, one sector, one store
     a.out.depth_radius[i] = make_float2(vz, radius);
     return out;
 }
@@ -515,8 +514,8 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
     __syncthreads();
     const uint32_t base = (uint32_t)s_base;
 
-    // ---- emission: each thread takes groups of four CONSECUTIVE global slots (aligned to 4, so a full group is two 16-byte
-    // stores): one binary search finds the Gaussian owning the first slot, the next slots walk forward — the next tile of the
+    // ---- emission: each thread takes groups of four CONSECUTIVE global slots (aligned to 4, so a full group is one 32-byte
+    // store): one binary search finds the Gaussian owning the first slot, the next slots walk forward — the next tile of the
     // same rectangle (x+1, wrapping to the next row) or the first tile of the next Gaussian. The reference loops serially
     // per Gaussian; here big and small splats cost the same per pair.
     const uint32_t slot_end = base + total;
@@ -559,9 +558,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
             }
         }
         if (lo == G0 && hi == G0 + 4u && G0 + 4u <= a.capacity) {
-            ulonglong2* kp = reinterpret_cast<ulonglong2*>(a.keys + G0);
-            kp[0] = make_ulonglong2(key[0], key[1]);
-            kp[1] = make_ulonglong2(key[2], key[3]);
+            stg256(a.keys + G0, key[0], key[1], key[2], key[3]);
         } else {
 #pragma unroll
             for (uint32_t q = 0; q < 4; ++q) {

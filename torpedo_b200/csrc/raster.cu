@@ -158,8 +158,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
             float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
             if (idx < range.y) {
                 g = (uint32_t)__ldg(words + idx);
-                ra = __ldg(geo4 + (size_t)g * 2);
-                rb = __ldg(geo4 + (size_t)g * 2 + 1);
+                ldg256(geo4 + (size_t)g * 2, ra, rb);  // the 32-byte SplatGeo record: one sector, one load
                 const float xlo = ra.x - rb.z - tile_fx0, xhi = ra.x + rb.z - tile_fx0;  // bbox relative to the tile origin
                 const float ylo = ra.y - rb.w - tile_fy0, yhi = ra.y + rb.w - tile_fy0;
                 const bool left = xhi >= 0.0f && xlo <= 7.0f, right = xhi >= 8.0f && xlo <= 15.0f;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
     const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
     for (uint32_t k = threadIdx.x; k < num_passes * SORT_BINS; k += HIST_THREADS) (&h[0][0])[k] = 0;
     __syncthreads();
-    // Each thread takes HIST_KPT CONSECUTIVE elements (four 16-byte loads): the pairs of one Gaussian are adjacent in the
+    // Each thread takes HIST_KPT CONSECUTIVE elements (two 32-byte loads): the pairs of one Gaussian are adjacent in the
     // unsorted buffer and usually share the upper tile bits, so run-length encoding the digits in registers removes most
     // shared-memory atomics and nearly all same-address conflicts.
     const uint32_t chunk = HIST_THREADS * HIST_KPT;
@@ -85,10 +85,10 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
         uint64_t k[HIST_KPT];
         if (first + HIST_KPT <= n) {
 #pragma unroll
-            for (uint32_t j = 0; j < HIST_KPT / 2; ++j) {
-                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(keys + first) + j);
-                k[2 * j] = v.x;
-                k[2 * j + 1] = v.y;
+            for (uint32_t j = 0; j < HIST_KPT / 4; ++j) {
+                uint64_t v[4];
+                ldg256(keys + first + 4 * j, v);
+                k[4 * j] = v[0]; k[4 * j + 1] = v[1]; k[4 * j + 2] = v[2]; k[4 * j + 3] = v[3];
             }
         } else {
 #pragma unroll
