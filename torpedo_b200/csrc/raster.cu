@@ -17,38 +17,36 @@ __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
     const uint64_t* __restrict__ keys = a.plan->final_sel ? a.keys[1] : a.keys[0];
     const uint32_t tshift = 32u + a.plan->tile_shift;  // words are (tile << shift | top depth bits) << 32 | Gaussian index
     uint2* ranges = reinterpret_cast<uint2*>(a.ranges);
-    // two keys per thread with one 16-byte load; the key before the pair comes from the neighbour's line (L1 hit)
-    const uint32_t pairs2 = (n + 1) / 2;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < pairs2; t += gridDim.x * blockDim.x) {
-        const uint32_t idx = 2 * t;
-        uint64_t k0, k1 = 0;
-        if (idx + 1 < n) {
-            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(keys) + t);
-            k0 = v.x;
-            k1 = v.y;
+    // four words per thread with one 32-byte load; the word before the group comes from the neighbour's sector (L1 hit)
+    const uint32_t groups = (n + 3) / 4;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < groups; t += gridDim.x * blockDim.x) {
+        const uint32_t idx = 4 * t;
+        uint64_t k[4];
+        if (idx + 4 <= n) {
+            ldg256(keys + idx, k);
         } else {
-            k0 = keys[idx];
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) k[q] = idx + q < n ? keys[idx + q] : 0ull;
         }
-        const uint32_t t0 = (uint32_t)(k0 >> tshift);
-        if (idx == 0) {
-            ranges[t0].x = 0;
-        } else {
-            const uint32_t prev = (uint32_t)(keys[idx - 1] >> tshift);
-            if (t0 != prev) { ranges[prev].y = idx; ranges[t0].x = idx; }
-        }
-        if (idx + 1 < n) {
-            const uint32_t t1 = (uint32_t)(k1 >> tshift);
-            if (t1 != t0) { ranges[t0].y = idx + 1; ranges[t1].x = idx + 1; }
-            if (idx + 1 == n - 1) ranges[t1].y = n;
-        } else {
-            ranges[t0].y = n;  // idx == n - 1
+        uint32_t prev = idx == 0 ? 0xffffffffu : (uint32_t)(keys[idx - 1] >> tshift);
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            if (idx + q < n) {
+                const uint32_t tq = (uint32_t)(k[q] >> tshift);
+                if (tq != prev) {
+                    if (idx + q != 0) ranges[prev].y = idx + q;
+                    ranges[tq].x = idx + q;
+                }
+                if (idx + q == n - 1) ranges[tq].y = n;
+                prev = tq;
+            }
         }
     }
 }
 
 cudaError_t launch_ranges(const RasterLaunch& a, uint32_t capacity, cudaStream_t s) {
     if (capacity == 0) return cudaSuccess;
-    uint32_t grid = (capacity / 2 + 255) / 256;
+    uint32_t grid = (capacity / 4 + 256) / 256;
     if (grid > 148u * 8u) grid = 148u * 8u;
     ranges_kernel<<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
