@@ -373,14 +373,25 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
 
     // ---- write-out: position i of the locally sorted tile goes to global_base[digit] + i (contiguous per bin) ---------
     uint32_t pos[OUT_PAIRS ? SORT_KPT : 1];
+    if (full) {  // every tile but the last: no per-key bounds branch
 #pragma unroll
-    for (uint32_t k = 0; k < SORT_KPT; ++k) {
-        const uint32_t i = tid + k * SORT_THREADS;
-        if (i < n_valid) {
+        for (uint32_t k = 0; k < SORT_KPT; ++k) {
+            const uint32_t i = tid + k * SORT_THREADS;
             const uint64_t kk = sm.keys[i];
             const uint32_t p = sm.global_base[digit_out(kk)] + i;
             if (OUT_PAIRS) pos[k] = p;
             dst_keys[p] = kk;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t k = 0; k < SORT_KPT; ++k) {
+            const uint32_t i = tid + k * SORT_THREADS;
+            if (i < n_valid) {
+                const uint64_t kk = sm.keys[i];
+                const uint32_t p = sm.global_base[digit_out(kk)] + i;
+                if (OUT_PAIRS) pos[k] = p;
+                dst_keys[p] = kk;
+            }
         }
     }
     if (OUT_PAIRS) {
