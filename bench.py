@@ -174,7 +174,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "ms/frame", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "pairs": pairs, "stages_ms": stages, "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -373,14 +373,30 @@ def run_gpu(args):
             ms, cpu_pairs, cpu_stages, cores = cpu_frames(g, ubos[0], 3, 1)
             line["cpu_baseline"] = {"value": ms, "unit": "ms/frame", "cores": cores, "kind": "port",
                                     "sample": "3 full frames (after 1 warm-up) of the same 6M-Gaussian scene, view 0", "stages_ms": cpu_stages}
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries print on stdout too (NCCL writes "NCCL version ..." there when NCCL_DEBUG is set): keep the original stdout
+    # for the JSON line and send everything else, C-level writes included, to stderr.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
