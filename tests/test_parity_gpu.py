@@ -439,3 +439,40 @@ def test_two_frames_in_flight_match_serial_rendering(E, oracle):
         assert (copies[k].cpu().numpy() == serial[k]).all(), k
     assert (eng.draw() == serial[-1]).all()
     eng.close()
+
+
+def test_blend_dispatch_order_never_changes_the_image(E, oracle):
+    """The blend processes tiles by decreasing expected cost (list length, then the splats it consumed on that tile in an
+    earlier frame): a scheduling hint. The same view rendered with no hints, with its own hints and with another view's
+    hints gives the same bytes, equal to a fresh context's and within tolerance of the oracle; a resize drops the hints."""
+    from torpedo_b200 import scenes
+    w, h = 400, 240  # 25 x 15 tiles: dense centre, sparse border, so the order really differs from image order
+    g = scenes.garden(30000, seed=17, log_scale_mean=-3.2)
+    cams = []
+    for theta, radius in ((0.4, 4.0), (2.9, 2.5)):
+        cam = E.PerspectiveCamera(w, h)
+        cam.look_at(E.to_cartesian(theta, 0.9, radius), (0, 0, 0), (0, 0, 1))
+        cams.append(cam.pack())
+    scene = E.Scene()
+    scene.add_group(g)
+    eng = E.GaussianEngine(w, h)
+    eng.compile(scene)
+    eng.set_frames_in_flight(1)
+    imgs = []
+    for u in (cams[0], cams[0], cams[1], cams[0]):  # no hints | own hints | (other view) | the other view's hints
+        eng.raster_ubo(u, 3)
+        imgs.append(eng.draw().copy())
+    assert (imgs[0] == imgs[1]).all() and (imgs[0] == imgs[3]).all()
+    ref = oracle.render(g, cams[0], w, h, 3)
+    assert (eng.read_ranges() == ref.ranges).all()
+    assert np.abs(imgs[0].astype(np.int32) - ref.rgba.astype(np.int32)).max() <= 1
+    assert (imgs[0][..., 3] == 255).all()
+    eng.resize(w // 2, h // 2)  # other tile grid: hints of the old one must not be used
+    eng.raster_ubo(cams[1], 3)
+    small = eng.draw().copy()
+    eng.close()
+    fresh = E.GaussianEngine(w // 2, h // 2)
+    fresh.compile(scene)
+    fresh.raster_ubo(cams[1], 3)
+    assert (fresh.draw() == small).all()
+    fresh.close()

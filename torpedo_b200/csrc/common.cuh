@@ -255,6 +255,8 @@ struct RasterLaunch {
     const float4* color;
     const float2* depth_radius;
     uint32_t* ranges;                     // zeroed, tiles x 2
+    uint32_t* order;                      // tiles: tile ids by decreasing expected cost, the blend's dispatch order
+    uint32_t* tile_cost;                  // tiles: splats the blend consumed per tile in an earlier frame (0: unknown); a hint
     uint8_t* out;
     size_t pitch;
     uint32_t width, height;

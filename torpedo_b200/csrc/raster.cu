@@ -44,11 +44,72 @@ __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// blend order: tiles by decreasing expected cost (longest processing time first)
+//
+// The blend's cost per tile is the number of splats it consumes before its last pixel saturates (mean 320, max 4.2 k on
+// the headline scene, lists: mean 1.9 k, max 20.8 k), the heaviest tile alone costs about what an average CTA slot
+// processes in the whole kernel, and the hardware dispatches CTAs in blockIdx order: in image order the heavy tiles of
+// the picture's centre start half-way through and the kernel ends on their tail (ncu: issue slots 65 % busy while an SM
+// has work, 46 % over the kernel). A counting sort of the tiles into 256 log-scale buckets (8 per octave) gives the
+// dispatch order; one CTA, ~8 us. Expected cost: what the blend consumed on this tile in an earlier frame of this context
+// (+50 %, a renderer's consecutive views are close), capped by the list length; the list length alone before that.
+// The order changes when a tile is processed, never what is computed for it.
+// ---------------------------------------------------------------------------------------------------
+
+constexpr uint32_t ORDER_THREADS = 1024;
+constexpr uint32_t ORDER_BUCKETS = 256;
+
+__device__ __forceinline__ uint32_t order_bucket(uint32_t len) {
+    const uint32_t w = 32u - __clz(len);                                 // bit length, 0 for an empty tile
+    const uint32_t sub = w >= 4u ? (len >> (w - 4u)) & 7u : (len << (4u - w)) & 7u;  // the three bits below the leading one
+    return ORDER_BUCKETS - 1u - min(w * 8u + sub, ORDER_BUCKETS - 1u);  // bucket 0 = longest lists
+}
+
+__global__ void __launch_bounds__(ORDER_THREADS) tile_order_kernel(RasterLaunch a, uint32_t tiles) {
+    __shared__ uint32_t s_off[ORDER_BUCKETS];
+    __shared__ uint32_t s_warp[ORDER_BUCKETS / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint2* __restrict__ ranges = reinterpret_cast<const uint2*>(a.ranges);
+    if (tid < ORDER_BUCKETS) s_off[tid] = 0;
+    __syncthreads();
+    auto expected = [&](uint32_t t) {
+        const uint2 r = ranges[t];
+        const uint32_t len = r.y - r.x, seen = a.tile_cost[t];
+        return seen ? min(len, seen + seen / 2u + 256u) : len;
+    };
+    for (uint32_t t = tid; t < tiles; t += ORDER_THREADS) atomicAdd(&s_off[order_bucket(expected(t))], 1u);
+    __syncthreads();
+    uint32_t c = 0, incl = 0;
+    if (tid < ORDER_BUCKETS) {
+        c = s_off[tid];
+        incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += up;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+    }
+    __syncthreads();
+    if (tid < ORDER_BUCKETS) {
+        uint32_t before = 0;
+        for (uint32_t w2 = 0; w2 < warp; ++w2) before += s_warp[w2];
+        s_off[tid] = before + incl - c;
+    }
+    __syncthreads();
+    for (uint32_t t = tid; t < tiles; t += ORDER_THREADS)
+        a.order[atomicAdd(&s_off[order_bucket(expected(t))], 1u)] = t;   // order inside a bucket is irrelevant
+}
+
 cudaError_t launch_ranges(const RasterLaunch& a, uint32_t capacity, cudaStream_t s) {
-    if (capacity == 0) return cudaSuccess;
-    uint32_t grid = (capacity / 4 + 256) / 256;
-    if (grid > 148u * 8u) grid = 148u * 8u;
-    ranges_kernel<<<grid, 256, 0, s>>>(a);
+    const uint32_t tiles = ((a.width + TILE_PX - 1) / TILE_PX) * ((a.height + TILE_PX - 1) / TILE_PX);
+    if (capacity != 0) {
+        uint32_t grid = (capacity / 4 + 256) / 256;
+        if (grid > 148u * 8u) grid = 148u * 8u;
+        ranges_kernel<<<grid, 256, 0, s>>>(a);
+    }
+    if (tiles != 0) tile_order_kernel<<<1, ORDER_THREADS, 0, s>>>(a, tiles);
     return cudaGetLastError();
 }
 
@@ -113,7 +174,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
     __shared__ BlendSmem sm;
 
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX;
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = a.order[blockIdx.x];  // longest lists first (tile_order_kernel)
     const uint32_t tile_x0 = (tile % gx) * TILE_PX, tile_y0 = (tile / gx) * TILE_PX;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // quadrant `warp`: origin (8*(warp&1), 8*(warp>>1)); lane -> pixel pair at (2*(lane&3), lane>>2) inside it
@@ -240,6 +301,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
         if (__syncthreads_and(u0 < 0.0f && u1 < 0.0f) || finished) break;
     }
 
+    if (tid == 0) a.tile_cost[tile] = max(min(in, range.y) - range.x, 1u);  // hint for the next frames' dispatch order
     if (inside & 1u)
         *reinterpret_cast<uint32_t*>(a.out + (size_t)y0 * a.pitch + (size_t)x0 * 4) =
             unorm8(r0) | (unorm8(g0) << 8) | (unorm8(b0) << 16) | 0xff000000u;

@@ -138,6 +138,8 @@ struct tpdcu_ctx {
     cudaStream_t capture_stream = nullptr;
 
     // target
+    uint32_t* tile_cost = nullptr;       // per tile: splats the blend consumed in an earlier frame (scheduling hint only)
+    uint32_t tile_cost_tiles = 0;
     uint32_t width = 0, height = 0;
     uint8_t* bound_out = nullptr;
     size_t bound_pitch = 0;
@@ -244,7 +246,7 @@ static int ensure_vals(FrameSlot& f) {  // value buffers of the standalone pair 
     return TPDCU_OK;
 }
 
-// The per-frame zeroed region: FrameCtl | preprocess scan descriptors | duplication scan descriptors | tile ranges |
+// The per-frame zeroed region: FrameCtl | preprocess scan descriptors | duplication scan descriptors | tile ranges + blend order |
 // look-back arrays of the depth sort | look-back arrays of the tile sort (last: the standalone sort may need more passes)
 static size_t lookback_bytes(const FrameSlot& f, uint32_t passes, uint32_t kind) {
     return align_up((size_t)std::max(passes, 1u) * sort_parts(f.capacity, kind) * SORT_BINS * sizeof(uint32_t), 256);
@@ -261,7 +263,7 @@ static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f, size_t lb_tile_bytes) 
     size_t off = align_up(sizeof(FrameCtl), 256);
     f.off_scan_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
     f.off_emit_desc = off; off = align_up(off + (size_t)emit_parts(c->n) * sizeof(uint64_t), 256);
-    f.off_ranges = off;    off = align_up(off + (size_t)tiles * 2 * sizeof(uint32_t), 256);
+    f.off_ranges = off;    off = align_up(off + (size_t)tiles * 3 * sizeof(uint32_t), 256);  // ranges (x2) | blend order
     f.off_lb_depth = off;  off = align_up(off + (size_t)sort_passes_for(32) * sort_parts(c->n, SORT_KIND_DEPTH) * SORT_BINS * sizeof(uint32_t), 256);
     f.off_lb_tile = off;   off += lb_tile_bytes;
     CK(cudaMalloc(&f.zero_region, off));
@@ -292,6 +294,21 @@ static int ensure_target(tpdcu_ctx* c, FrameSlot& f) {
 static int sync_slots(tpdcu_ctx* c) {
     for (auto& f : c->slots)
         if (f.stream) CK(cudaStreamSynchronize(f.stream));
+    return TPDCU_OK;
+}
+
+// Blend cost hints, one per tile, shared by the frame slots (they only steer the dispatch order). A new framebuffer size
+// starts without hints; ensure_zero_region drops the slots' graphs in that case, so no captured launch keeps the old pointer.
+static int ensure_tile_cost(tpdcu_ctx* c) {
+    const uint32_t tiles = tiles_of(c);
+    if (c->tile_cost && c->tile_cost_tiles == tiles) return TPDCU_OK;
+    if (int r = sync_slots(c)) return r;
+    cudaFree(c->tile_cost);
+    c->tile_cost = nullptr;
+    CK(cudaMalloc(&c->tile_cost, (size_t)std::max(tiles, 1u) * sizeof(uint32_t)));
+    CK(cudaMemset(c->tile_cost, 0, (size_t)std::max(tiles, 1u) * sizeof(uint32_t)));
+    c->tile_cost_tiles = tiles;
+    for (auto& f : c->slots) drop_graph(f);
     return TPDCU_OK;
 }
 
@@ -334,6 +351,7 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     const uint32_t tile_passes = sort_passes_for(tile_bits);
     const size_t lb_tile_bytes = lookback_bytes(f, tile_passes, SORT_KIND_TILE);
     if (int r = ensure_zero_region(c, f, lb_tile_bytes)) return r;
+    if (int r = ensure_tile_cost(c)) return r;
     const bool t = c->timing;
     cudaStream_t user = tk.user_stream;
     cudaStream_t s = t ? user : f.stream;
@@ -378,6 +396,8 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     ra.keys[0] = f.keys[0]; ra.keys[1] = f.keys[1];
     ra.plan = f.plan; ra.geo = f.geo; ra.color = f.color; ra.depth_radius = f.depth_radius;
     ra.ranges = reinterpret_cast<uint32_t*>(f.zero_region + f.off_ranges);
+    ra.order = ra.ranges + 2 * (size_t)tiles_of(c);
+    ra.tile_cost = c->tile_cost;
     ra.out = tk.out; ra.pitch = tk.pitch; ra.width = c->width; ra.height = c->height;
 
     if (t) CK(cudaEventRecord(c->ev[0], s));
@@ -621,6 +641,7 @@ void tpdcu_destroy(tpdcu_ctx* c) {
         if (f.done) cudaEventDestroy(f.done);
         if (f.read_done) cudaEventDestroy(f.read_done);
     }
+    cudaFree(c->tile_cost);
     if (c->capture_stream) cudaStreamDestroy(c->capture_stream);
     if (c->ext_mem) cudaDestroyExternalMemory(c->ext_mem);
     if (c->status) cudaFreeHost(c->status);
