@@ -179,6 +179,91 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
+// ---- spherical-harmonic colour (splat/common.slang:35-80, project.slang:82-83) -----------------
+//
+// Streaming form: the 48 coefficients of a Gaussian are consumed in memory order (float index f = 3 * coefficient + channel,
+// four per 16-byte plane), so only one plane has to be live at a time. Every operation is an explicitly rounded
+// __fmul_rn / __fadd_rn in the order of the reference's expression (terms added left to right, each term
+// (constant * basis) * coefficient), so the result does not depend on the translation unit's FMA contraction setting.
+// Band 3 keeps the reference's quirk: term 12 is "+ C3[3]*z*(2zz-3xx-3yy) + coefficient" (splat/common.slang:69).
+struct ShBasis {
+    float b[16];   // basis_k including its constant and sign: term_k = b[k] * coefficient_k  (k = 12: see above)
+};
+__device__ __forceinline__ ShBasis sh_basis(float x, float y, float z, int degree) {
+    constexpr float C0 = 0.28209479177387814f;
+    constexpr float C1 = 0.4886025119029199f;
+    constexpr float C2[5] = { 1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                              0.5462742152960396f };
+    constexpr float C3[7] = { -0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                              -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f };
+    ShBasis s;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s.b[k] = 0.0f;
+    s.b[0] = C0;
+    if (degree > 0) {
+        s.b[1] = __fmul_rn(C1, y);   // subtracted
+        s.b[2] = __fmul_rn(C1, z);
+        s.b[3] = __fmul_rn(C1, x);   // subtracted
+        if (degree > 1) {
+            const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+            const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), zx = __fmul_rn(z, x);
+            s.b[4] = __fmul_rn(C2[0], xy);
+            s.b[5] = __fmul_rn(C2[1], yz);
+            s.b[6] = __fmul_rn(C2[2], __fsub_rn(__fsub_rn(__fmul_rn(2.0f, zz), xx), yy));
+            s.b[7] = __fmul_rn(C2[3], zx);
+            s.b[8] = __fmul_rn(C2[4], __fsub_rn(xx, yy));
+            if (degree > 2) {
+                s.b[9] = __fmul_rn(__fmul_rn(C3[0], y), __fsub_rn(__fmul_rn(3.0f, xx), yy));
+                s.b[10] = __fmul_rn(__fmul_rn(C3[1], xy), z);
+                s.b[11] = __fmul_rn(__fmul_rn(C3[2], y), __fsub_rn(__fsub_rn(__fmul_rn(4.0f, zz), xx), yy));
+                s.b[12] = __fmul_rn(__fmul_rn(C3[3], z), __fsub_rn(__fsub_rn(__fmul_rn(2.0f, zz), __fmul_rn(3.0f, xx)), __fmul_rn(3.0f, yy)));
+                s.b[13] = __fmul_rn(__fmul_rn(C3[4], x), __fsub_rn(__fsub_rn(__fmul_rn(4.0f, zz), xx), yy));
+                s.b[14] = __fmul_rn(__fmul_rn(C3[5], z), __fsub_rn(xx, yy));
+                s.b[15] = __fmul_rn(__fmul_rn(C3[6], x), __fsub_rn(xx, __fmul_rn(3.0f, yy)));
+            }
+        }
+    }
+    return s;
+}
+// one coefficient (float index f) into its channel's running sum
+__device__ __forceinline__ void sh_accumulate(float (&acc)[3], const ShBasis& s, int f, float coef) {
+    const int k = f / 3, c = f % 3;
+    if (k == 0) acc[c] = __fmul_rn(s.b[0], coef);
+    else if (k == 1 || k == 3) acc[c] = __fsub_rn(acc[c], __fmul_rn(s.b[k], coef));
+    else if (k == 12) acc[c] = __fadd_rn(__fadd_rn(acc[c], s.b[12]), coef);
+    else acc[c] = __fadd_rn(acc[c], __fmul_rn(s.b[k], coef));
+}
+__host__ __device__ constexpr int sh_planes(int degree) { return degree <= 0 ? 1 : degree == 1 ? 3 : degree == 2 ? 7 : 12; }
+
+// colour of Gaussian g seen from the camera: normalize(mean - camera) with IEEE sqrt and division, SH, + 0.5, max 0
+__device__ __forceinline__ float3 sh_color(const float4* __restrict__ sh_row, float px, float py, float pz, const float* cam_pos,
+                                           int degree) {
+    float dx = __fsub_rn(px, cam_pos[0]), dy = __fsub_rn(py, cam_pos[1]), dz = __fsub_rn(pz, cam_pos[2]);
+    const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
+    const ShBasis s = sh_basis(dx, dy, dz, degree);
+    const int coefs = 3 * (degree <= 0 ? 1 : (degree + 1) * (degree + 1));
+    float acc[3] = { 0.0f, 0.0f, 0.0f };
+    // Two planes (one 32-byte sector) per load: a thread that walks its own row costs the L1 one tag look-up per
+    // request, and these rows are gathered (blend staging: 12 x 128-bit requests per splat made the L1 the bottleneck).
+#pragma unroll
+    for (int p = 0; p < (int)SH_PLANES; p += 2) {
+        if (p < sh_planes(degree)) {
+            float4 v, w;
+            ldg256(sh_row + p, v, w);  // p + 1 <= 11: inside the 192-byte row whatever the degree
+            if (4 * p + 0 < coefs) sh_accumulate(acc, s, 4 * p + 0, v.x);
+            if (4 * p + 1 < coefs) sh_accumulate(acc, s, 4 * p + 1, v.y);
+            if (4 * p + 2 < coefs) sh_accumulate(acc, s, 4 * p + 2, v.z);
+            if (4 * p + 3 < coefs) sh_accumulate(acc, s, 4 * p + 3, v.w);
+            if (4 * p + 4 < coefs) sh_accumulate(acc, s, 4 * p + 4, w.x);
+            if (4 * p + 5 < coefs) sh_accumulate(acc, s, 4 * p + 5, w.y);
+            if (4 * p + 6 < coefs) sh_accumulate(acc, s, 4 * p + 6, w.z);
+            if (4 * p + 7 < coefs) sh_accumulate(acc, s, 4 * p + 7, w.w);
+        }
+    }
+    return make_float3(fmaxf(__fadd_rn(acc[0], 0.5f), 0.0f), fmaxf(__fadd_rn(acc[1], 0.5f), 0.0f), fmaxf(__fadd_rn(acc[2], 0.5f), 0.0f));
+}
+
 // ---- host-side launchers (one per translation unit) ---------------------------------------------
 
 struct PreprocessLaunch {
@@ -252,11 +337,15 @@ struct RasterLaunch {
     const uint64_t* keys[2];              // words tile << 32 | index, sorted
     const SortPlan* plan;                 // of the tile sort
     const SplatGeo* geo;
-    const float4* color;
+    const float4* color;                  // introspection only: the frame evaluates colours inside the blend
     const float2* depth_radius;
     uint32_t* ranges;                     // zeroed, tiles x 2
-    uint32_t* order;                      // tiles: tile ids by decreasing expected cost, the blend's dispatch order
+    uint32_t* order;                      // 2 x tiles: tile ids by decreasing expected cost (the blend's dispatch order) | scratch
     uint32_t* tile_cost;                  // tiles: splats the blend consumed per tile in an earlier frame (0: unknown); a hint
+    const float4* posop;                  // scene: xyz + opacity (view direction of the SH colour)
+    const float4* sh;                     // scene: [n][SH_PLANES]
+    const FrameCam* cam;                  // camera position of this frame
+    uint32_t sh_degree;
     uint8_t* out;
     size_t pitch;
     uint32_t width, height;

@@ -57,6 +57,12 @@ __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
 // The order changes when a tile is processed, never what is computed for it.
 // ---------------------------------------------------------------------------------------------------
 
+// Splats of a tile's list the blend is expected to consume: what it consumed on that tile in an earlier frame of this
+// context + 50 % + 256, capped by the list; `unknown` entries when there is no such frame.
+__device__ __forceinline__ uint32_t expected_front(uint32_t len, uint32_t seen, uint32_t unknown) {
+    return seen ? min(len, seen + seen / 2u + 256u) : min(len, unknown);
+}
+
 constexpr uint32_t ORDER_THREADS = 1024;
 constexpr uint32_t ORDER_BUCKETS = 256;
 
@@ -75,10 +81,16 @@ __global__ void __launch_bounds__(ORDER_THREADS) tile_order_kernel(RasterLaunch 
     __syncthreads();
     auto expected = [&](uint32_t t) {
         const uint2 r = ranges[t];
-        const uint32_t len = r.y - r.x, seen = a.tile_cost[t];
-        return seen ? min(len, seen + seen / 2u + 256u) : len;
+        return expected_front(r.y - r.x, a.tile_cost[t], 0xffffffffu);
     };
-    for (uint32_t t = tid; t < tiles; t += ORDER_THREADS) atomicAdd(&s_off[order_bucket(expected(t))], 1u);
+    // The hints are written by the blends of other frames in flight while this kernel runs: read each one ONCE. (Counting
+    // with one value and scattering with another would leave `order` no permutation — a tile rendered twice, one never.)
+    uint32_t* bucket_of = a.order + tiles;
+    for (uint32_t t = tid; t < tiles; t += ORDER_THREADS) {
+        const uint32_t b = order_bucket(expected(t));
+        bucket_of[t] = b;
+        atomicAdd(&s_off[b], 1u);
+    }
     __syncthreads();
     uint32_t c = 0, incl = 0;
     if (tid < ORDER_BUCKETS) {
@@ -99,7 +111,7 @@ __global__ void __launch_bounds__(ORDER_THREADS) tile_order_kernel(RasterLaunch 
     }
     __syncthreads();
     for (uint32_t t = tid; t < tiles; t += ORDER_THREADS)
-        a.order[atomicAdd(&s_off[order_bucket(expected(t))], 1u)] = t;   // order inside a bucket is irrelevant
+        a.order[atomicAdd(&s_off[bucket_of[t]], 1u)] = t;   // order inside a bucket is irrelevant; same thread wrote bucket_of[t]
 }
 
 cudaError_t launch_ranges(const RasterLaunch& a, uint32_t capacity, cudaStream_t s) {
@@ -184,6 +196,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
     const float tile_fx0 = (float)tile_x0, tile_fy0 = (float)tile_y0;
 
     const uint64_t* __restrict__ words = a.plan->final_sel ? a.keys[1] : a.keys[0];
+    const float cam_pos[3] = { a.cam->cam_pos[0], a.cam->cam_pos[1], a.cam->cam_pos[2] };
     const uint2 range = reinterpret_cast<const uint2*>(a.ranges)[tile];
     const float4* __restrict__ geo4 = reinterpret_cast<const float4*>(a.geo);
 
@@ -247,7 +260,14 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
             }
             if (keep) {
                 const uint32_t pos = qn + before[0] + __popc(ballot[0] & lanemask_lt());
-                const float4 col = __ldg(a.color + g);
+                // Colour on demand: the blend only ever stages the front of every list before its pixels saturate (19 % of
+                // the visible Gaussians on the headline scene), so the SH colour (project.slang:82-83) is evaluated here,
+                // for the splats that reach a queue, instead of by a kernel over all visible Gaussians (that kernel ran at
+                // the HBM roofline: 1.2 GB per frame, 0.19 ms; here 0.56 GB are gathered inside a kernel that is not
+                // memory-bound). Same arithmetic as the introspection kernel (sh_color / eval_sh).
+                const float4 po = __ldg(a.posop + g);
+                const float3 c3 = sh_color(a.sh + (size_t)g * SH_PLANES, po.x, po.y, po.z, cam_pos, (int)a.sh_degree);
+                const float4 col = make_float4(c3.x, c3.y, c3.z, 0.0f);
                 sm.ent[pos].g0 = make_float4(ra.x, ra.y, (-0.5f * LOG2E) * ra.z, -LOG2E * ra.w);
                 sm.ent[pos].g1 = make_float4((-0.5f * LOG2E) * rb.x, rb.y, -__log2f(255.0f * rb.y) - 0.01f, 0.0f);
                 sm.ent[pos].col = col;

@@ -263,7 +263,7 @@ static int ensure_zero_region(tpdcu_ctx* c, FrameSlot& f, size_t lb_tile_bytes) 
     size_t off = align_up(sizeof(FrameCtl), 256);
     f.off_scan_desc = off; off = align_up(off + (size_t)pre_parts * sizeof(uint64_t), 256);
     f.off_emit_desc = off; off = align_up(off + (size_t)emit_parts(c->n) * sizeof(uint64_t), 256);
-    f.off_ranges = off;    off = align_up(off + (size_t)tiles * 3 * sizeof(uint32_t), 256);  // ranges (x2) | blend order
+    f.off_ranges = off;    off = align_up(off + (size_t)tiles * 4 * sizeof(uint32_t), 256);  // ranges (x2) | blend order | its buckets
     f.off_lb_depth = off;  off = align_up(off + (size_t)sort_passes_for(32) * sort_parts(c->n, SORT_KIND_DEPTH) * SORT_BINS * sizeof(uint32_t), 256);
     f.off_lb_tile = off;   off += lb_tile_bytes;
     CK(cudaMalloc(&f.zero_region, off));
@@ -307,6 +307,7 @@ static int ensure_tile_cost(tpdcu_ctx* c) {
     c->tile_cost = nullptr;
     CK(cudaMalloc(&c->tile_cost, (size_t)std::max(tiles, 1u) * sizeof(uint32_t)));
     CK(cudaMemset(c->tile_cost, 0, (size_t)std::max(tiles, 1u) * sizeof(uint32_t)));
+    CK(cudaDeviceSynchronize());  // the slots' streams do not synchronise with the stream the memset ran on
     c->tile_cost_tiles = tiles;
     for (auto& f : c->slots) drop_graph(f);
     return TPDCU_OK;
@@ -326,8 +327,7 @@ struct FrameLaunch {
 static int enqueue_middle(tpdcu_ctx* c, FrameSlot& f, const FrameLaunch& l, cudaStream_t s, bool timing) {
     CK(cudaMemsetAsync(f.zero_region, 0, l.zero_bytes, s));
     if (timing) CK(cudaEventRecord(c->ev[1], s));
-    CK(launch_preprocess(l.pre, s));
-    CK(launch_color(l.pre, s));
+    CK(launch_preprocess(l.pre, s));   // the SH colour is evaluated by the blend, for the splats it stages
     if (timing) CK(cudaEventRecord(c->ev[2], s));
     CK(launch_sort(l.depth_sort, 0, s, nullptr));
     if (timing) CK(cudaEventRecord(c->ev[3], s));
@@ -398,6 +398,7 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     ra.ranges = reinterpret_cast<uint32_t*>(f.zero_region + f.off_ranges);
     ra.order = ra.ranges + 2 * (size_t)tiles_of(c);
     ra.tile_cost = c->tile_cost;
+    ra.posop = c->posop; ra.sh = c->sh; ra.cam = f.cam; ra.sh_degree = l.pre.sh_degree;
     ra.out = tk.out; ra.pitch = tk.pitch; ra.width = c->width; ra.height = c->height;
 
     if (t) CK(cudaEventRecord(c->ev[0], s));
@@ -862,6 +863,15 @@ int tpdcu_read_splats(tpdcu_ctx* c, void* host_splats48, uint32_t n) {
     if (int r = finish_internal(c)) return r;
     if (n == 0) return TPDCU_OK;
     FrameSlot& f = last(c);
+    {   // The frame itself computes colours on demand inside the blend; the reference's Splat records carry the colour of
+        // every visible Gaussian, so the introspection export evaluates them all first (same arithmetic, sh_color/eval_sh).
+        PreprocessLaunch p{};
+        p.scene = SceneArrays{ c->posop, c->cov_a, c->cov_b, c->sh, c->entity_count > 1 ? c->entity : nullptr, c->n, c->entity_count };
+        p.cam = f.cam;
+        p.out = SplatArrays{ f.geo, f.color, f.depth_radius, f.rect, f.offsets };
+        p.width = c->width; p.height = c->height; p.sh_degree = std::min(c->newest.sh_degree, 3u);
+        CK(launch_color(p, f.stream));
+    }
     void* tmp = nullptr;
     CK(cudaMalloc(&tmp, (size_t)n * TPDCU_SPLAT_BYTES));
     cudaError_t e = launch_export_splats(SplatArrays{ f.geo, f.color, f.depth_radius, f.rect, f.offsets }, n, tmp, f.stream);
