@@ -476,3 +476,26 @@ def test_blend_dispatch_order_never_changes_the_image(E, oracle):
     fresh.raster_ubo(cams[1], 3)
     assert (fresh.draw() == small).all()
     fresh.close()
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_every_sh_degree_on_demand_colour(E, oracle, deg):
+    """The frame evaluates the SH colour inside the blend, for the splats it stages; tpdcu_read_splats evaluates it for
+    every visible Gaussian with a kernel of its own. Both must agree with the oracle at every degree (the planes of a
+    row a degree does not use hold non-zero coefficients here)."""
+    from torpedo_b200 import scenes
+    w, h = 320, 200
+    g = scenes.garden(12000, seed=40 + deg, log_scale_mean=-3.4, sh_rest_std=0.2)
+    cam = E.PerspectiveCamera(w, h)
+    cam.look_at((2.4, -2.9, 2.2), (0, 0, 0), (0, 0, 1))
+    eng, img, ref = render_both(E, oracle, g, cam.pack(), w, h, deg)
+    assert np.abs(img.astype(np.int32) - ref.rgba.astype(np.int32)).max() <= 1
+    assert psnr(img[..., :3], ref.rgba[..., :3]) >= 50.0
+    splats = eng.read_splats(len(g))
+    vis = ref.tiles > 0
+    got, want = f32(splats[vis, 0:3]), f32(ref.splats[vis, 0:3])
+    assert np.allclose(got, want, rtol=2e-6, atol=2e-6)
+    # a second frame after the export still renders the same image (the export's colour kernel shares the slot's arrays)
+    eng.raster_ubo(cam.pack(), deg)
+    assert (eng.draw() == img).all()
+    eng.close()
