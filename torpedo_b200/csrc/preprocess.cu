@@ -193,6 +193,12 @@ __device__ __forceinline__ uint64_t lookback_exclusive(const uint64_t* desc, uin
     return exclusive;
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct Projected {
     uint32_t count, depth_bits;
 };
@@ -263,14 +269,15 @@ __device__ __forceinline__ Projected project_one(const PreprocessLaunch& a, uint
     // power >= -t, t = ln(255*opacity), is the ellipse d^T conic d <= 2t whose bounding box is sqrt(2t*cov). Used ONLY to
     // skip splats that cannot touch a tile; the margins cover fp32 rounding of power/exp in the blend. Ill-conditioned
     // covariances are never culled.
+    // (approximate log and square roots: their errors, ~1e-6 relative, are far inside the margins)
     float ext_x = 3.0e38f, ext_y = 3.0e38f;
-    const float t = logf(255.0f * po.w);
+    const float t = __logf(255.0f * po.w);
     if (!(t >= 0.0f)) {
         ext_x = ext_y = -1.0e30f;  // opacity < 1/255: alpha < 1/255 at every pixel
     } else if (det > 1e-3f * (cvx * cvz) && cvx > 0.0f && cvz > 0.0f) {
         const float tt = 2.0f * (t + 0.02f);
-        ext_x = sqrtf(tt * cvx) * 1.0002f + 0.02f;
-        ext_y = sqrtf(tt * cvz) * 1.0002f + 0.02f;
+        ext_x = sqrt_approx(tt * cvx) * 1.0002f + 0.02f;
+        ext_y = sqrt_approx(tt * cvz) * 1.0002f + 0.02f;
     }
     stg256(reinterpret_cast<float4*>(a.out.geo + i), make_float4(px, py, cvz * det_inv, -cvy * det_inv),
            make_float4(cvx * det_inv, po.w, ext_x, ext_y));  // the 32-byte SplatGeo record, one sector, one store
@@ -365,24 +372,21 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
         if (lane == 31) s_warp_tot[k][warp] = incl[k];
     }
     __syncthreads();
-    uint64_t total = 0;  // running (visible, pairs) total of the groups handled so far
-    uint64_t local_excl[PRE_ITEMS];
-#pragma unroll
-    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
-        uint64_t warp_excl = 0, group_total = 0;
-#pragma unroll
-        for (uint32_t w = 0; w < PRE_THREADS / 32; ++w) {
-            const uint64_t t = s_warp_tot[k][w];
-            if (w < warp) warp_excl += t;
-            group_total += t;
-        }
-        local_excl[k] = total + warp_excl + incl[k] - mine[k];
-        total += group_total;
-    }
 
-    // ---- decoupled look-back across partitions (warp 0) ---------------------------------------------
+    // ---- warp 0: exclusive scan of the PRE_ITEMS x 8 (group, warp) totals (group-major: the order of the Gaussians), then
+    // the decoupled look-back across partitions ----------------------------------------------------------------------
     const uint32_t num_parts = (n + PRE_PART - 1) / PRE_PART;
     if (warp == 0) {
+        static_assert(PRE_ITEMS * (PRE_THREADS / 32) == 32, "one lane per (group, warp) total");
+        const uint64_t mine_tot = (&s_warp_tot[0][0])[lane];
+        uint64_t incl_tot = mine_tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t up = __shfl_up_sync(0xffffffffu, incl_tot, d);
+            if (lane >= (uint32_t)d) incl_tot += up;
+        }
+        (&s_warp_tot[0][0])[lane] = incl_tot - mine_tot;  // exclusive prefix of this (group, warp) inside the partition
+        const uint64_t total = __shfl_sync(0xffffffffu, incl_tot, 31);
         uint64_t exclusive = 0;
         if (part == 0) {
             if (lane == 0) st_relaxed_u64(a.scan_desc, ((uint64_t)FLAG_PREFIX << 62) | total);
@@ -402,6 +406,9 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
         }
     }
     __syncthreads();
+    uint64_t local_excl[PRE_ITEMS];
+#pragma unroll
+    for (uint32_t k = 0; k < PRE_ITEMS; ++k) local_excl[k] = s_warp_tot[k][warp] + incl[k] - mine[k];
     const uint64_t base = s_base;
 #pragma unroll
     for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
