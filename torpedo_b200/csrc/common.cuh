@@ -235,14 +235,34 @@ __device__ __forceinline__ void sh_accumulate(float (&acc)[3], const ShBasis& s,
 }
 __host__ __device__ constexpr int sh_planes(int degree) { return degree <= 0 ? 1 : degree == 1 ? 3 : degree == 2 ? 7 : 12; }
 
-// colour of Gaussian g seen from the camera: normalize(mean - camera) with IEEE sqrt and division, SH, + 0.5, max 0
-__device__ __forceinline__ float3 sh_color(const float4* __restrict__ sh_row, float px, float py, float pz, const float* cam_pos,
-                                           int degree) {
+// view direction of the colour: normalize(mean - camera position) with IEEE sqrt and division (project.slang:82)
+__device__ __forceinline__ float3 sh_direction(float px, float py, float pz, const float* cam_pos) {
     float dx = __fsub_rn(px, cam_pos[0]), dy = __fsub_rn(py, cam_pos[1]), dz = __fsub_rn(pz, cam_pos[2]);
     const float len = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-    dx = __fdiv_rn(dx, len); dy = __fdiv_rn(dy, len); dz = __fdiv_rn(dz, len);
-    const ShBasis s = sh_basis(dx, dy, dz, degree);
-    const int coefs = 3 * (degree <= 0 ? 1 : (degree + 1) * (degree + 1));
+    return make_float3(__fdiv_rn(dx, len), __fdiv_rn(dy, len), __fdiv_rn(dz, len));
+}
+// two consecutive planes (eight coefficients from float index 4 * p) into the running sums
+__device__ __forceinline__ void sh_accumulate_planes(float (&acc)[3], const ShBasis& s, int p, int coefs, const float4& v, const float4& w) {
+    if (4 * p + 0 < coefs) sh_accumulate(acc, s, 4 * p + 0, v.x);
+    if (4 * p + 1 < coefs) sh_accumulate(acc, s, 4 * p + 1, v.y);
+    if (4 * p + 2 < coefs) sh_accumulate(acc, s, 4 * p + 2, v.z);
+    if (4 * p + 3 < coefs) sh_accumulate(acc, s, 4 * p + 3, v.w);
+    if (4 * p + 4 < coefs) sh_accumulate(acc, s, 4 * p + 4, w.x);
+    if (4 * p + 5 < coefs) sh_accumulate(acc, s, 4 * p + 5, w.y);
+    if (4 * p + 6 < coefs) sh_accumulate(acc, s, 4 * p + 6, w.z);
+    if (4 * p + 7 < coefs) sh_accumulate(acc, s, 4 * p + 7, w.w);
+}
+__host__ __device__ constexpr int sh_coefs(int degree) { return 3 * (degree <= 0 ? 1 : (degree + 1) * (degree + 1)); }
+__device__ __forceinline__ float3 sh_finish(const float (&acc)[3]) {  // + 0.5, max 0 (splat/common.slang:79-80)
+    return make_float3(fmaxf(__fadd_rn(acc[0], 0.5f), 0.0f), fmaxf(__fadd_rn(acc[1], 0.5f), 0.0f), fmaxf(__fadd_rn(acc[2], 0.5f), 0.0f));
+}
+
+// colour of a Gaussian seen from the camera, its SH row read from global memory
+__device__ __forceinline__ float3 sh_color(const float4* __restrict__ sh_row, float px, float py, float pz, const float* cam_pos,
+                                           int degree) {
+    const float3 d = sh_direction(px, py, pz, cam_pos);
+    const ShBasis s = sh_basis(d.x, d.y, d.z, degree);
+    const int coefs = sh_coefs(degree);
     float acc[3] = { 0.0f, 0.0f, 0.0f };
     // Two planes (one 32-byte sector) per load: a thread that walks its own row costs the L1 one tag look-up per
     // request, and these rows are gathered (blend staging: 12 x 128-bit requests per splat made the L1 the bottleneck).
@@ -251,17 +271,10 @@ __device__ __forceinline__ float3 sh_color(const float4* __restrict__ sh_row, fl
         if (p < sh_planes(degree)) {
             float4 v, w;
             ldg256(sh_row + p, v, w);  // p + 1 <= 11: inside the 192-byte row whatever the degree
-            if (4 * p + 0 < coefs) sh_accumulate(acc, s, 4 * p + 0, v.x);
-            if (4 * p + 1 < coefs) sh_accumulate(acc, s, 4 * p + 1, v.y);
-            if (4 * p + 2 < coefs) sh_accumulate(acc, s, 4 * p + 2, v.z);
-            if (4 * p + 3 < coefs) sh_accumulate(acc, s, 4 * p + 3, v.w);
-            if (4 * p + 4 < coefs) sh_accumulate(acc, s, 4 * p + 4, w.x);
-            if (4 * p + 5 < coefs) sh_accumulate(acc, s, 4 * p + 5, w.y);
-            if (4 * p + 6 < coefs) sh_accumulate(acc, s, 4 * p + 6, w.z);
-            if (4 * p + 7 < coefs) sh_accumulate(acc, s, 4 * p + 7, w.w);
+            sh_accumulate_planes(acc, s, p, coefs, v, w);
         }
     }
-    return make_float3(fmaxf(__fadd_rn(acc[0], 0.5f), 0.0f), fmaxf(__fadd_rn(acc[1], 0.5f), 0.0f), fmaxf(__fadd_rn(acc[2], 0.5f), 0.0f));
+    return sh_finish(acc);
 }
 
 // ---- host-side launchers (one per translation unit) ---------------------------------------------

@@ -120,48 +120,7 @@ cudaError_t launch_setup(const PreprocessLaunch& a, const CameraUbo& ubo, cudaSt
 }
 
 // ---------------------------------------------------------------------------------------------------
-// spherical harmonics (splat/common.slang:35-80), colour is tolerance-checked only
-// ---------------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ float3 eval_sh(const float* shf, float x, float y, float z, int degree) {
-    constexpr float C0 = 0.28209479177387814f;
-    constexpr float C1 = 0.4886025119029199f;
-    constexpr float C2[5] = { 1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
-                              0.5462742152960396f };
-    constexpr float C3[7] = { -0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
-                              -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f };
-    float out[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        auto F = [&](int k) { return shf[3 * k + c]; };
-        float result = C0 * F(0);
-        if (degree > 0) {
-            result = ((result - C1 * y * F(1)) + C1 * z * F(2)) - C1 * x * F(3);
-            if (degree > 1) {
-                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, zx = z * x;
-                result = ((((result + C2[0] * xy * F(4)) + C2[1] * yz * F(5)) + C2[2] * (2.0f * zz - xx - yy) * F(6)) +
-                          C2[3] * zx * F(7)) +
-                         C2[4] * (xx - yy) * F(8);
-                if (degree > 2) {
-                    // term 12 is "C3[3]*z*(2zz-3xx-3yy) + feature" in the reference (splat/common.slang:69)
-                    result = (((((((result + C3[0] * y * (3.0f * xx - yy) * F(9)) + C3[1] * xy * z * F(10)) +
-                                  C3[2] * y * (4.0f * zz - xx - yy) * F(11)) +
-                                 C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy)) +
-                                F(12)) +
-                               C3[4] * x * (4.0f * zz - xx - yy) * F(13)) +
-                              C3[5] * z * (xx - yy) * F(14)) +
-                             C3[6] * x * (xx - 3.0f * yy) * F(15);
-                }
-            }
-        }
-        result += 0.5f;
-        out[c] = fmaxf(result, 0.0f);
-    }
-    return make_float3(out[0], out[1], out[2]);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// fused geometry + scan + duplication kernel (no colour: see color_kernel below)
+// geometry + scan + visible compaction kernel (no colour: the blend evaluates it on demand, raster.cu)
 // ---------------------------------------------------------------------------------------------------
 
 // Scan descriptor: [63:62] state | [61:32] visible-Gaussian count | [31:0] pair count.
@@ -585,10 +544,11 @@ cudaError_t launch_emit(const EmitLaunch& a, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// colour: SH evaluation for the visible Gaussians only (project.slang:82-83, splat/common.slang:35-80). No look-back, no
-// block barrier: a pure stream of 16 B position + up to 192 B of SH in, 16 B out, DRAM-bound. Every visible Gaussian's SH
-// row is pulled into shared memory by ONE bulk-copy (TMA) instruction issued by its own thread — exact 32-byte sectors, no
-// bytes fetched for culled neighbours, and the load instructions of a 48-float gather disappear.
+// colour of EVERY visible Gaussian (project.slang:82-83, splat/common.slang:35-80): introspection only (tpdcu_read_splats).
+// A frame evaluates the colour inside the blend, for the splats it stages (raster.cu); this kernel was the frame's colour
+// stage before that and ran at the HBM roofline: a pure stream of 16 B position + up to 192 B of SH in, 16 B out, every
+// visible Gaussian's SH row pulled into shared memory by ONE bulk-copy (TMA) instruction issued by its own thread — exact
+// 32-byte sectors, no bytes fetched for culled neighbours.
 // ---------------------------------------------------------------------------------------------------
 
 constexpr uint32_t COLOR_THREADS = 128;
@@ -619,12 +579,11 @@ __global__ void __launch_bounds__(COLOR_THREADS) color_kernel(PreprocessLaunch a
                          (uint32_t)__cvta_generic_to_shared(row)),
                      "l"(a.scene.sh + (size_t)i * SH_PLANES), "r"((uint32_t)(PLANES * 16)), "r"(bar)
                      : "memory");
-    float dx = 0.f, dy = 0.f, dz = 0.f;
+    float3 dir = make_float3(0.f, 0.f, 0.f);
     if (vis) {
         const float4 po = __ldg(a.scene.posop + i);
-        dx = po.x - a.cam->cam_pos[0]; dy = po.y - a.cam->cam_pos[1]; dz = po.z - a.cam->cam_pos[2];
-        const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
-        dx /= len; dy /= len; dz /= len;
+        const float cam_pos[3] = { a.cam->cam_pos[0], a.cam->cam_pos[1], a.cam->cam_pos[2] };
+        dir = sh_direction(po.x, po.y, po.z, cam_pos);
     }
     {
         uint32_t ready = 0;
@@ -632,13 +591,16 @@ __global__ void __launch_bounds__(COLOR_THREADS) color_kernel(PreprocessLaunch a
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(ready) : "r"(bar) : "memory");
     }
     if (!vis) return;
-    float shf[48];
+    // the arithmetic of the blend's on-demand colour (sh_color), the row coming from shared memory
+    const ShBasis s = sh_basis(dir.x, dir.y, dir.z, DEG);
+    float acc[3] = { 0.0f, 0.0f, 0.0f };
 #pragma unroll
-    for (int p = 0; p < PLANES; ++p) {
+    for (int p = 0; p < PLANES; p += 2) {
         const float4 v = row[p];
-        shf[4 * p + 0] = v.x; shf[4 * p + 1] = v.y; shf[4 * p + 2] = v.z; shf[4 * p + 3] = v.w;
+        const float4 w = p + 1 < PLANES ? row[p + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        sh_accumulate_planes(acc, s, p, sh_coefs(DEG), v, w);
     }
-    const float3 col = eval_sh(shf, dx, dy, dz, DEG);
+    const float3 col = sh_finish(acc);
     a.out.color[i] = make_float4(col.x, col.y, col.z, 0.0f);
 }
 

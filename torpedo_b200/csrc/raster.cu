@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
                 // the visible Gaussians on the headline scene), so the SH colour (project.slang:82-83) is evaluated here,
                 // for the splats that reach a queue, instead of by a kernel over all visible Gaussians (that kernel ran at
                 // the HBM roofline: 1.2 GB per frame, 0.19 ms; here 0.56 GB are gathered inside a kernel that is not
-                // memory-bound). Same arithmetic as the introspection kernel (sh_color / eval_sh).
+                // memory-bound). Same arithmetic as the introspection kernel (common.cuh: sh_basis / sh_accumulate).
                 const float4 po = __ldg(a.posop + g);
                 const float3 c3 = sh_color(a.sh + (size_t)g * SH_PLANES, po.x, po.y, po.z, cam_pos, (int)a.sh_degree);
                 const float4 col = make_float4(c3.x, c3.y, c3.z, 0.0f);

@@ -864,7 +864,7 @@ int tpdcu_read_splats(tpdcu_ctx* c, void* host_splats48, uint32_t n) {
     if (n == 0) return TPDCU_OK;
     FrameSlot& f = last(c);
     {   // The frame itself computes colours on demand inside the blend; the reference's Splat records carry the colour of
-        // every visible Gaussian, so the introspection export evaluates them all first (same arithmetic, sh_color/eval_sh).
+        // every visible Gaussian, so the introspection export evaluates them all first (same arithmetic: sh_basis / sh_accumulate of common.cuh).
         PreprocessLaunch p{};
         p.scene = SceneArrays{ c->posop, c->cov_a, c->cov_b, c->sh, c->entity_count > 1 ? c->entity : nullptr, c->n, c->entity_count };
         p.cam = f.cam;
