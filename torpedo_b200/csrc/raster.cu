@@ -138,7 +138,9 @@ cudaError_t launch_ranges(const RasterLaunch& a, uint32_t capacity, cudaStream_t
 
 constexpr uint32_t BLEND_THREADS = 128;
 constexpr uint32_t BLEND_WARPS = BLEND_THREADS / 32;
-constexpr uint32_t BLEND_QUEUE = 256;
+// One staging pass per fill: with the colour evaluated at staging, every splat staged beyond the point where the tile
+// saturates costs an SH evaluation (a 256-entry queue, two passes per fill, measured 3 % slower).
+constexpr uint32_t BLEND_QUEUE = 128;
 constexpr float LOG2E = 1.4426950408889634f;
 static_assert(BLEND_WARPS == 4, "one warp per 8x8 quadrant of the 16x16 tile");
 
