@@ -87,6 +87,52 @@ out.append(run("3a synthetic 6M SH3 1080p (headline)", g6, 1920, 1080, 3, camera
 out.append(run("3b synthetic 6M SH3 2160p", g6, 3840, 2160, 3, camera(3840, 2160, (2.8, 2.8, 2.6))))
 out.append(run("4 VolumeSplatting dense 2M SH2 720p", scenes.dense_volume(2_000_000, seed=4), 1280, 720, 2,
                camera(1280, 720, (-2.0, -1.0, 0.0), (0, 0, 0), (0, -1, 0)), model=scenes.VOLUME_TRANSFORM))
+
+
+def run_view_batch(name, g, w, h, deg, n_views, radius, check_views=(0, 21, 42, 63)):
+    """BASELINE config 5 on one GPU: a batch of views of one scene through tpdcu_raster_views (frames stay in HBM), the
+    batch timed with CUDA events; the sampled views are compared with the oracle image."""
+    import torch
+    scene = E.Scene()
+    scene.add_group(g)
+    eng = E.GaussianEngine(w, h)
+    eng.compile(scene, E.Settings(deg))
+    ubos = np.stack([camera(w, h, E.to_cartesian(2.0 * np.pi * k / n_views, 0.9, radius)).pack() for k in range(n_views)])
+    frames = torch.zeros((n_views, h, w, 4), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):  # warm-up: buffers grow to the largest view
+        eng.raster_views(ubos, frames.data_ptr(), h * w * 4, deg, stream)
+        eng.finish()
+    times = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        eng.raster_views(ubos, frames.data_ptr(), h * w * 4, deg, stream)
+        e1.record()
+        eng.finish()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    res = {"config": name, "n": int(g.shape[0]), "w": w, "h": h, "sh": deg, "views": n_views, "ms_per_batch": round(ms, 3),
+           "ms_per_view": round(ms / n_views, 4), "views_per_s": round(n_views / ms * 1e3, 1)}
+    if not skip_parity:
+        out_frames = frames.cpu().numpy()
+        worst, off, pairs = 0, 0, []
+        for k in check_views:
+            ref = O.render(g, ubos[k], w, h, deg)
+            d = np.abs(out_frames[k].astype(np.int32) - ref.rgba.astype(np.int32))
+            worst = max(worst, int(d[..., :3].max()))
+            off += int((d[..., :3].max(axis=-1) > 0).sum())
+            pairs.append(int(ref.pairs))
+        res["parity"] = {"views_checked": list(check_views), "max_abs_rgb_lsb": worst, "pixels_off_by_one": off, "pairs": pairs}
+    eng.close()
+    print(json.dumps(res), flush=True)
+    return res
+
+
+out.append(run_view_batch("5 64 views x 3M SH3 1080p, one GPU (ring, radius 5)", scenes.garden(3_000_000, 5, log_scale_mean=bench.LOG_SCALE_MEAN),
+                          1920, 1080, 3, 64, 5.0))
 os.makedirs("gpurun_out", exist_ok=True)
 with open("gpurun_out/configs_r1.json", "w") as f:
     json.dump(out, f, indent=1)
