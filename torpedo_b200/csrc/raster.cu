@@ -65,6 +65,7 @@ __device__ __forceinline__ uint32_t expected_front(uint32_t len, uint32_t seen, 
 
 constexpr uint32_t ORDER_THREADS = 1024;
 constexpr uint32_t ORDER_BUCKETS = 256;
+constexpr uint32_t ORDER_UNROLL = 8;
 
 __device__ __forceinline__ uint32_t order_bucket(uint32_t len) {
     const uint32_t w = 32u - __clz(len);                                 // bit length, 0 for an empty tile
@@ -79,17 +80,28 @@ __global__ void __launch_bounds__(ORDER_THREADS) tile_order_kernel(RasterLaunch 
     const uint2* __restrict__ ranges = reinterpret_cast<const uint2*>(a.ranges);
     if (tid < ORDER_BUCKETS) s_off[tid] = 0;
     __syncthreads();
-    auto expected = [&](uint32_t t) {
-        const uint2 r = ranges[t];
-        return expected_front(r.y - r.x, a.tile_cost[t], 0xffffffffu);
-    };
     // The hints are written by the blends of other frames in flight while this kernel runs: read each one ONCE. (Counting
     // with one value and scattering with another would leave `order` no permutation — a tile rendered twice, one never.)
     uint32_t* bucket_of = a.order + tiles;
-    for (uint32_t t = tid; t < tiles; t += ORDER_THREADS) {
-        const uint32_t b = order_bucket(expected(t));
-        bucket_of[t] = b;
-        atomicAdd(&s_off[b], 1u);
+    // one CTA, so the global loads are the critical path: ORDER_UNROLL tiles per thread in flight at a time
+    for (uint32_t t0 = tid; t0 < tiles; t0 += ORDER_THREADS * ORDER_UNROLL) {
+        uint2 r[ORDER_UNROLL];
+        uint32_t seen[ORDER_UNROLL];
+#pragma unroll
+        for (uint32_t k = 0; k < ORDER_UNROLL; ++k) {
+            const uint32_t t = t0 + k * ORDER_THREADS;
+            r[k] = t < tiles ? ranges[t] : make_uint2(0u, 0u);
+            seen[k] = t < tiles ? a.tile_cost[t] : 0u;
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < ORDER_UNROLL; ++k) {
+            const uint32_t t = t0 + k * ORDER_THREADS;
+            if (t < tiles) {
+                const uint32_t b = order_bucket(expected_front(r[k].y - r[k].x, seen[k], 0xffffffffu));
+                bucket_of[t] = b;
+                atomicAdd(&s_off[b], 1u);
+            }
+        }
     }
     __syncthreads();
     uint32_t c = 0, incl = 0;
