@@ -81,9 +81,10 @@ int tpdcu_bind_output_fd(tpdcu_ctx* ctx, int fd, size_t bytes);
 
 /* ---- per-frame hot path: GaussianEngine::rasterFrame (GaussianEngine.cpp:621-712) -------------- */
 
-/* One frame: camera upload (updateCameraBuffer :764-775) -> preprocess+scan+duplication (project.slang,
- * prefix.slang, keygen.slang) -> 64-bit onesweep sort (radix-*.slang x23) -> tile ranges (range.slang)
- * -> blending (blend.slang). `camera_ubo` is the reference's 136-byte Camera block. Enqueued on `stream`
+/* One frame: camera upload (updateCameraBuffer :764-775) -> geometry + scan (project.slang, prefix.slang)
+ * -> depth sort of the visible Gaussians -> duplication in depth order (keygen.slang) -> sort of the pairs
+ * by tile (together: radix-*.slang x23) -> tile ranges (range.slang) -> blending (blend.slang), which also
+ * evaluates the SH colour (splat/common.slang:35-80) of the splats it stages. `camera_ubo` is the reference's 136-byte Camera block. Enqueued on `stream`
  * without any host synchronisation: unlike the reference (:662-674) the pair count P is never read back
  * mid-frame. If P turns out to exceed the pair-buffer capacity the frame is re-rendered after growing
  * the buffers inside the next tpdcu_finish()/tpdcu_read_*() call. */
@@ -115,7 +116,8 @@ int tpdcu_frames_repeated(tpdcu_ctx* ctx, uint32_t* count);
 int tpdcu_get_counts(tpdcu_ctx* ctx, uint32_t* pairs, uint32_t* visible);
 /* Splat buffer in the REFERENCE layout (48 B each, `tiles` holding the exclusive offset as after
  * prefix.slang). Fields other than radius/tiles of culled Gaussians are zero (the reference leaves
- * them stale, project.slang:34-35). */
+ * them stale, project.slang:34-35). A frame only evaluates the colour of the splats its blend stages;
+ * this call evaluates it for every visible Gaussian first (same arithmetic). */
 int tpdcu_read_splats(tpdcu_ctx* ctx, void* host_splats48, uint32_t n);
 /* Sorted keys / values (first P entries) and per-tile (start,end) ranges. */
 int tpdcu_read_keys(tpdcu_ctx* ctx, uint64_t* host_keys, uint32_t count);
