@@ -499,3 +499,45 @@ def test_every_sh_degree_on_demand_colour(E, oracle, deg):
     eng.raster_ubo(cam.pack(), deg)
     assert (eng.draw() == img).all()
     eng.close()
+
+
+def test_many_frames_in_flight_keep_every_tile(E, oracle):
+    """Regression: the blend's dispatch order is built from cost hints that the blends of OTHER frames in flight rewrite
+    at the same time. Built from two different reads of a hint, the order was once no permutation: a tile rendered twice,
+    another never (stale pixels of an older frame). 1080p (8160 tiles), 128 frames over four very different views, three
+    in flight, each into its own buffer pre-filled with a sentinel: every frame must equal the serial rendering of its
+    view."""
+    import torch
+    from torpedo_b200 import scenes
+    from torpedo_b200._lib import check, tpdcu
+    w, h = 1920, 1080
+    g = scenes.garden(150000, seed=23, log_scale_mean=-4.2)
+    scene = E.Scene()
+    scene.add_group(g)
+    eng = E.GaussianEngine(w, h)
+    eng.compile(scene)
+    ubos = []
+    for theta, phi, radius in ((0.2, 0.9, 4.5), (1.9, 0.5, 2.2), (3.6, 1.3, 7.0), (5.1, 0.9, 1.4)):
+        cam = E.PerspectiveCamera(w, h)
+        cam.look_at(E.to_cartesian(theta, phi, radius), (0, 0, 0), (0, 0, 1))
+        ubos.append(cam.pack())
+    eng.set_frames_in_flight(1)
+    serial = []
+    for u in ubos:
+        eng.raster_ubo(u, 3)
+        serial.append(torch.from_numpy(eng.draw().copy()).cuda())
+    eng.set_frames_in_flight(3)
+    n_slots, n_frames = 16, 128
+    frames = torch.empty((n_slots, h, w, 4), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for base in range(0, n_frames, n_slots):
+        frames.fill_(0x5a)
+        for j in range(n_slots):
+            check(tpdcu().tpdcu_bind_output_device_ptr(eng.ctx, frames[j].data_ptr(), w * 4))
+            eng.raster_ubo(ubos[((base + j) * 3) % 4], 3, stream)
+        eng.finish()
+        torch.cuda.synchronize()
+        for j in range(n_slots):
+            assert torch.equal(frames[j], serial[((base + j) * 3) % 4]), base + j
+    check(tpdcu().tpdcu_bind_output_device_ptr(eng.ctx, None, 0))
+    eng.close()
