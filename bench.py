@@ -230,11 +230,19 @@ def run_gpu(args):
     from torpedo_b200._lib import check, tpdcu
     lib = tpdcu()
 
-    def render_steps(first_step, count):
+    GATHER_CHUNK = 4  # frames per asynchronous gather: the transfer of one chunk overlaps the rendering of the next
+
+    def render_steps(first_step, count, gather=False):
+        pending = []
         for s in range(count):
             view = (first_step + s) * world + rank
             check(lib.tpdcu_bind_output_device_ptr(eng.ctx, frames[s].data_ptr(), WIDTH * 4))
             eng.raster_ubo(ubos[view % RING_VIEWS], SH_DEGREE, stream)
+            if gather and world > 1 and ((s + 1) % GATHER_CHUNK == 0 or s + 1 == count):
+                c0 = s + 1 - ((s % GATHER_CHUNK) + 1)
+                pending.append(dist.gather(frames[c0:s + 1], [gt[c0:s + 1] for gt in gathered] if rank == 0 else None, dst=0, async_op=True))
+        for work in pending:
+            work.wait()  # the current stream waits for the transfers; the host does not
 
     ubos = [ubo_for(v) for v in range(RING_VIEWS)]
 
@@ -247,10 +255,8 @@ def run_gpu(args):
     for v in range(rank, RING_VIEWS, max(world, 1) * 4):
         eng.raster_ubo(ubos[v], SH_DEGREE, stream)
         eng.finish()
-    render_steps(0, min(W, K))
+    render_steps(0, min(W, K), gather=True)
     eng.finish()
-    if world > 1:
-        dist.gather(frames, gathered, dst=0)
     barrier()
 
     # ---- timed region: K frames per rank (+ the NCCL frame gather at N > 1) -----------------------------------------
@@ -260,9 +266,7 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    render_steps(W, K)
-    if world > 1:
-        dist.gather(frames, gathered, dst=0)
+    render_steps(W, K, gather=True)
     ev1.record()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)

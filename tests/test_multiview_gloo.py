@@ -40,6 +40,11 @@ def _worker(rank, world, port, n_views, result_path):
 
         frames = mv.render_views(render_batch, n_views, 4, 6, dev)
         assert rendered == mv.views_of_rank(n_views, rank, world)
+        # chunked: every chunk's gather is started asynchronously behind its rendering; same result, same render order
+        rendered.clear()
+        chunked = mv.render_views(render_batch, n_views, 4, 6, dev, chunk=2)
+        assert rendered == mv.views_of_rank(n_views, rank, world)
+        assert (chunked is None) == (frames is None) and (frames is None or torch.equal(chunked, frames))
         if rank == 0:
             assert frames.shape == (n_views, 4, 6, 4)
             for v in range(n_views):

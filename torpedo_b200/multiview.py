@@ -61,13 +61,34 @@ def gather_frames(local_frames: torch.Tensor, n_views: int, dst: int = 0) -> tor
 
 
 def render_views(render_batch: Callable[[Sequence[int], torch.Tensor], None], n_views: int, height: int, width: int,
-                 device: torch.device, dst: int = 0) -> torch.Tensor | None:
+                 device: torch.device, dst: int = 0, chunk: int = 0) -> torch.Tensor | None:
     """Shard `n_views` over the ranks, let `render_batch(view_ids, out)` fill this rank's slots (out[k] <- view_ids[k]),
-    then gather. `render_batch` is the only place pixels are produced (GaussianEngine.raster_views on the GPU box)."""
+    then gather. `render_batch` is the only place pixels are produced (GaussianEngine.raster_views on the GPU box).
+
+    chunk > 0: render `chunk` slots at a time and start the gather of each chunk asynchronously, so that the transfer of
+    one chunk overlaps the rendering of the next; the result is the same tensor."""
     world, rank = dist.get_world_size(), dist.get_rank()
     mine = views_of_rank(n_views, rank, world)
     slots = -(-n_views // world)
     local = torch.zeros((slots, height, width, 4), dtype=torch.uint8, device=device)
-    if mine:
-        render_batch(mine, local[: len(mine)])
-    return gather_frames(local, n_views, dst)
+    if chunk <= 0 or world == 1:
+        if mine:
+            render_batch(mine, local[: len(mine)])
+        return gather_frames(local, n_views, dst)
+    parts = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
+    pending = []
+    for s0 in range(0, slots, chunk):
+        s1 = min(s0 + chunk, slots)
+        ids = mine[s0:s1]
+        if ids:
+            render_batch(ids, local[s0:s0 + len(ids)])
+        pending.append(dist.gather(local[s0:s1], [p[s0:s1] for p in parts] if rank == dst else None, dst=dst, async_op=True))
+    for work in pending:
+        work.wait()
+    if rank != dst:
+        return None
+    out = torch.empty((n_views,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for v in range(n_views):
+        r, s = owner_of_view(v, world)
+        out[v] = parts[r][s]
+    return out
