@@ -359,6 +359,12 @@ def run_gpu(args):
             "sort_gkeys_per_s": stage_pairs / (sort_ms * 1e-3) / 1e9 if sort_ms > 0 else None,
             "sort": dict(sort_info, design="two-level: visible Gaussians by depth, duplication in depth order, pairs by tile",
                          bytes_per_pair=8 + 16 * passes, bytes_per_visible_gaussian=8 + 16 * depth_passes),
+            # share of one frame alone per stage, and what bounds it (ncu: profiles/r1_s3_ncu_*.txt). The blend is the largest
+            # stage and is bound by SM issue slots and L1 gathers, not by HBM or tensor throughput; the roofline object below
+            # is therefore about the largest HBM-bound kernel, the onesweep pass (6 launches, a quarter of the frame).
+            "stage_shares": {k: round(stages[k] / stages["frame"], 3) for k in ("preprocess", "depth_sort", "duplicate", "tile_sort", "ranges", "blend")},
+            "stage_bounds": {"preprocess": "issue / barrier (HBM 35 %)", "depth_sort": "latency (L2-resident, two waves of tiles)", "duplicate": "latency / LSU",
+                             "tile_sort": "hbm (onesweep passes) + smem atomics (histogram)", "ranges": "hbm", "blend": "SM issue + L1 gathers (on-demand SH colour inside)"},
             "roofline": {"kernel": "onesweep_kernel<WORDS> (one 8-bit digit pass of the tile sort over the pair words; average over the passes of a frame)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": ncu_traffic_per_launch(), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pass_ms,
@@ -367,7 +373,7 @@ def run_gpu(args):
                     "steps": e2e_steps, "checksum": checksum, "serial_latency_ms": e2e_serial_ms / e2e_steps,
                     "frames_repeated": repeats,
                     "note": "lookAt on host -> rasterFrame -> drawAsync into pinned host memory, frames in flight as in the reference's loop"},
-            # per frame: setup, preprocess, colour, duplication, ranges, blend, 2 x (histogram, plan) + one onesweep launch per
+            # per frame: setup, preprocess, duplication, ranges, blend order, blend, 2 x (histogram, plan) + one onesweep launch per
             # 8-bit digit of the widest possible key of each sort: 4 for the 32 depth bits (a pass whose digit is constant
             # still launches and exits), ceil(tile_bits / 8) for the tiles
             "gpu_launches": K * (10 + 4 + ((((WIDTH + 15) // 16 * ((HEIGHT + 15) // 16) - 1).bit_length() + 7) // 8)),
