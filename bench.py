@@ -373,10 +373,10 @@ def run_gpu(args):
                     "steps": e2e_steps, "checksum": checksum, "serial_latency_ms": e2e_serial_ms / e2e_steps,
                     "frames_repeated": repeats,
                     "note": "lookAt on host -> rasterFrame -> drawAsync into pinned host memory, frames in flight as in the reference's loop"},
-            # per frame: setup, preprocess, duplication, ranges, blend order, blend, 2 x (histogram, plan) + one onesweep launch per
+            # per frame: setup, preprocess, duplication, ranges, blend order, blend, 2 x histogram (+ plan) + one onesweep launch per
             # 8-bit digit of the widest possible key of each sort: 4 for the 32 depth bits (a pass whose digit is constant
             # still launches and exits), ceil(tile_bits / 8) for the tiles
-            "gpu_launches": K * (10 + 4 + ((((WIDTH + 15) // 16 * ((HEIGHT + 15) // 16) - 1).bit_length() + 7) // 8)),
+            "gpu_launches": K * (8 + 4 + ((((WIDTH + 15) // 16 * ((HEIGHT + 15) // 16) - 1).bit_length() + 7) // 8)),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -36,6 +36,8 @@ constexpr uint32_t SORT_WARPS = SORT_THREADS / 32;
 
 // Tickets and digit histograms of one radix sort.
 struct SortCtl {
+    uint32_t hist_done;                   // histogram CTAs that have added their counts (the last one makes the plan)
+    uint32_t pad[3];
     uint32_t ticket[SORT_MAX_PASSES];
     uint32_t hist[SORT_MAX_PASSES][SORT_BINS];  // global digit histograms (then exclusive offsets)
 };

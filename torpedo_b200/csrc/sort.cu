@@ -67,10 +67,13 @@ __host__ __device__ __forceinline__ uint32_t passes_needed(uint32_t total_bits) 
 // up-front histogram of every digit (one read of the keys)
 // ---------------------------------------------------------------------------------------------------
 
+__device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, SortPlan* plan, uint32_t kind, uint32_t n_host,
+                                          uint32_t capacity, uint32_t end_bit, uint32_t tile_bits);
+
 template <bool WORDS>
 __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t* __restrict__ keys, const FrameCtl* frame, SortCtl* ctl,
-                                                                  uint32_t kind, uint32_t n_host, uint32_t capacity, uint32_t end_bit,
-                                                                  uint32_t tile_bits) {
+                                                                  SortPlan* plan, uint32_t kind, uint32_t n_host, uint32_t capacity,
+                                                                  uint32_t end_bit, uint32_t tile_bits) {
     __shared__ uint32_t h[SORT_MAX_PASSES][SORT_BINS];
     const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit, tile_bits);
     const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
@@ -122,35 +125,51 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
         const uint32_t c = (&h[0][0])[k];
         if (c) atomicAdd(&ctl->hist[0][0] + k, c);
     }
+    // The last CTA to get here turns the histograms into the plan (exclusive digit offsets, passes to skip, ping-pong
+    // schedule): one launch and one kernel boundary less per sort than a plan kernel of its own.
+    __shared__ uint32_t s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->hist_done, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        make_plan(frame, ctl, plan, kind, n_host, capacity, end_bit, tile_bits);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // plan: exclusive digit offsets, identity-pass detection, ping-pong schedule
 // ---------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(const FrameCtl* frame, SortCtl* ctl, SortPlan* plan, uint32_t kind,
-                                                               uint32_t n_host, uint32_t capacity, uint32_t end_bit, uint32_t tile_bits) {
+// Runs in ONE CTA of at least SORT_BINS threads; every thread of the CTA must call it (block barriers inside), the first
+// SORT_BINS threads own one bin each. The histograms are read with gpu-scope loads: other CTAs produced them.
+__device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, SortPlan* plan, uint32_t kind, uint32_t n_host,
+                                          uint32_t capacity, uint32_t end_bit, uint32_t tile_bits) {
     __shared__ uint32_t s_warp[SORT_BINS / 32];
     __shared__ uint32_t s_skip[SORT_MAX_PASSES];
     const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit, tile_bits);
     const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
     const uint32_t b = threadIdx.x, lane = b & 31u, warp = b >> 5;
+    const bool owner = b < SORT_BINS;
     if (b < SORT_MAX_PASSES) s_skip[b] = 0;
     __syncthreads();
     for (uint32_t p = 0; p < num_passes; ++p) {
-        const uint32_t c = ctl->hist[p][b];
-        if (c == n) s_skip[p] = 1;  // every key falls in this bin (also true for n == 0)
+        const uint32_t c = owner ? ld_relaxed_u32(&ctl->hist[p][b]) : 0u;
+        if (owner && c == n) s_skip[p] = 1;  // every key falls in this bin (also true for n == 0)
         uint32_t incl = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= (uint32_t)d) incl += up;
         }
-        if (lane == 31) s_warp[warp] = incl;
+        if (owner && lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        uint32_t wex = 0;
-        for (uint32_t w = 0; w < warp; ++w) wex += s_warp[w];
-        ctl->hist[p][b] = wex + incl - c;
+        if (owner) {
+            uint32_t wex = 0;
+            for (uint32_t w = 0; w < warp; ++w) wex += s_warp[w];
+            ctl->hist[p][b] = wex + incl - c;
+        }
         __syncthreads();
     }
     if (b == 0) {
@@ -169,6 +188,12 @@ __global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(const FrameCtl* fr
         plan->total_bits = sp.total_bits;
         plan->tile_shift = kind == SORT_KIND_TILE ? depth_split(frame, tile_bits).extra : 0u;
     }
+}
+
+// stand-alone form: sorts with nothing to count (no elements, no key bits)
+__global__ void __launch_bounds__(SORT_BINS) sort_plan_kernel(const FrameCtl* frame, SortCtl* ctl, SortPlan* plan, uint32_t kind,
+                                                               uint32_t n_host, uint32_t capacity, uint32_t end_bit, uint32_t tile_bits) {
+    make_plan(frame, ctl, plan, kind, n_host, capacity, end_bit, tile_bits);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -461,9 +486,8 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     uint32_t hist_grid = (bound + chunk - 1) / chunk;
     const uint32_t hist_max = (uint32_t)a.sm_count * 4u;
     if (hist_grid > hist_max) hist_grid = hist_max;
-    if (words) sort_hist_kernel<true><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
-    else sort_hist_kernel<false><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
-    sort_plan_kernel<<<1, SORT_BINS, 0, s>>>(a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
+    if (words) sort_hist_kernel<true><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
+    else sort_hist_kernel<false><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
     if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
     const uint32_t parts = sort_parts(bound, a.kind);
     const uint32_t parts_cap = sort_parts(a.capacity, a.kind);
