@@ -205,7 +205,19 @@ def ref_lib() -> C.CDLL:
         _ref.tpdref_sizeof_gaussian_point.restype = C.c_uint32
         _ref.tpdref_normalize4.restype = None
         _ref.tpdref_normalize4.argtypes = [C.c_void_p, C.c_void_p]
+        _ref.tpdref_from_model.restype = C.c_int64
+        _ref.tpdref_from_model.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
     return _ref
+
+
+def ref_from_model(ply_path: str) -> np.ndarray:
+    """The reference's own GaussianPoint::fromModel (GaussianGeometry.cpp:59-127 + miniply.cpp, compiled in place)."""
+    n = ref_lib().tpdref_from_model(ply_path.encode(), None, 0)
+    if n < 0:
+        raise RuntimeError(f"the reference's fromModel threw on {ply_path}")
+    out = np.zeros((n, GAUSSIAN_FLOATS), dtype=np.float32)
+    ref_lib().tpdref_from_model(ply_path.encode(), _p(out), n)
+    return out
 
 
 def ref_camera_ubo(width, height, eye, center, up, fov_deg=0.0, near=0.0, far=0.0) -> np.ndarray:

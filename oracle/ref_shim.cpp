@@ -5,6 +5,7 @@
 //   /root/reference/torpedo/extension/src/PerspectiveCamera.cpp     (updateProjectionMatrix, :9-23)
 //   /root/reference/torpedo/math/include/torpedo/math/*.h           (compensated dot/cross/mul)
 //   /root/reference/torpedo/volumetric/include/.../GaussianGeometry.h (GaussianPoint, rgb2sh)
+//   /root/reference/torpedo/volumetric/src/GaussianGeometry.cpp      (GaussianPoint::fromModel, :59-127) + src/miniply.cpp
 // The sources are compiled where they lie (see oracle/Makefile, target _ref); nothing is copied.
 // The shim packs the camera UBO exactly like GaussianEngine::updateCameraBuffer
 // (/root/reference/torpedo/volumetric/src/GaussianEngine.cpp:764-775).
@@ -54,5 +55,20 @@ void tpdref_normalize4(const float in4[4], float out4[4]) {
 }
 
 uint32_t tpdref_sizeof_gaussian_point() { return sizeof(tpd::GaussianPoint); }
+
+// GaussianPoint::fromModel (volumetric/src/GaussianGeometry.cpp:59-127) on a 3DGS .ply file: the reference's own reader
+// (miniply) and field transforms. Returns the point count (records beyond `capacity` are not copied), or -1 when the
+// reference throws.
+int64_t tpdref_from_model(const char* ply_path, float* out_recs60, uint64_t capacity) {
+    try {
+        const auto points = tpd::GaussianPoint::fromModel(ply_path);
+        static_assert(sizeof(tpd::GaussianPoint) == 240);
+        const auto n = std::min<uint64_t>(points.size(), capacity);
+        if (n && out_recs60) std::memcpy(out_recs60, points.data(), n * sizeof(tpd::GaussianPoint));
+        return static_cast<int64_t>(points.size());
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
 
 } // extern "C"

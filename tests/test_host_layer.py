@@ -143,5 +143,39 @@ def test_from_model_matches_reference_field_transforms(E, oracle, tmp_path, rest
         assert (got.view(np.uint32) == want.view(np.uint32)).all()
     else:
         np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    if oracle.ref_available():  # this container: the reference's own fromModel + miniply, compiled in place (oracle/_ref)
+        ref = oracle.ref_from_model(path)
+        assert (got.view(np.uint32) == ref.view(np.uint32)).all()
     with pytest.raises(E.TpdError):
         E.from_model(str(tmp_path / "missing.ply"))
+
+
+PLY_FIXTURES = ["sh3_binary", "sh2_binary", "sh0_binary", "sh3_ascii", "sh1_mixed_types", "sh2_shuffled"]
+
+
+@pytest.mark.parametrize("name", PLY_FIXTURES)
+def test_from_model_matches_the_reference_on_committed_ply_fixtures(E, name):
+    """tests/golden/ply/<name>.ref.npy holds what the REFERENCE's own GaussianPoint::fromModel (GaussianGeometry.cpp:59-127
+    with its miniply reader, compiled from /root/reference into oracle/_ref) returned for <name>.ply
+    (tests/golden/make_ply_golden.py). The drop-in's own reader must produce the same 240-byte records bit for bit:
+    binary and ASCII bodies, double / uchar columns, a face element after the vertices, CRLF headers, shuffled property
+    order (the reference takes the properties FOLLOWING f_dc_2 as the rest coefficients, :89-92)."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ply")
+    want = np.load(os.path.join(here, name + ".ref.npy"))
+    got = E.from_model(os.path.join(here, name + ".ply"))
+    assert got.shape == want.shape == (64, 60)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+    assert (got[:, 11] == 1.0).all()                                   # scale modifier (:115)
+    np.testing.assert_allclose(np.linalg.norm(got[:, 4:8], axis=1), 1.0, atol=1e-6)
+
+
+def test_ply_fixtures_still_match_oracle_ref(oracle):
+    """Only where /root/reference is present: the committed .ref.npy files are what the reference returns today."""
+    import os
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ply")
+    for name in PLY_FIXTURES:
+        ref = oracle.ref_from_model(os.path.join(here, name + ".ply"))
+        assert (ref.view(np.uint32) == np.load(os.path.join(here, name + ".ref.npy")).view(np.uint32)).all(), name

@@ -541,3 +541,92 @@ def test_many_frames_in_flight_keep_every_tile(E, oracle):
             assert torch.equal(frames[j], serial[((base + j) * 3) % 4]), base + j
     check(tpdcu().tpdcu_bind_output_device_ptr(eng.ctx, None, 0))
     eng.close()
+
+
+def test_overflowing_older_frame_leaves_the_newest_frame_newest(E, oracle):
+    """Three frames in flight; of two frames enqueued back to back only the FIRST overflows the grow-only pair buffers. The
+    repeat of that frame (after growth) must not become what draw / read_sorted / read_ranges describe: they refer to the
+    newest frame, whose intermediate buffers may have been re-allocated by the growth (it is rendered again too)."""
+    from torpedo_b200 import scenes
+    w, h = 320, 192
+    g = scenes.garden(30000, seed=71, log_scale_mean=-3.4)
+    scene = E.Scene()
+    scene.add_group(g)
+    near, far = E.PerspectiveCamera(w, h), E.PerspectiveCamera(w, h)
+    near.look_at(E.to_cartesian(0.3, 0.9, 2.0), (0, 0, 0), (0, 0, 1))
+    far.look_at(E.to_cartesian(0.3, 0.9, 14.0), (0, 0, 0), (0, 0, 1))
+    ref_near = oracle.render(g, near.pack(), w, h, 3)
+    ref_far = oracle.render(g, far.pack(), w, h, 3)
+    eng = E.GaussianEngine(w, h)
+    eng.compile(scene)
+    eng.set_frames_in_flight(3)
+    for _ in range(3):  # every slot sized by the far view only
+        eng.raster_frame(far)
+    eng.finish()
+    cap = eng.capacity()
+    assert ref_far.pairs <= cap < ref_near.pairs, (ref_far.pairs, cap, ref_near.pairs)
+    before = eng.frames_repeated()
+    eng.raster_frame(near)  # overflows
+    eng.raster_frame(far)   # does not; this is the newest frame
+    img = eng.draw()
+    assert eng.frames_repeated() > before
+    assert eng.counts()[0] == ref_far.pairs
+    keys, vals = eng.read_sorted()
+    assert (keys == ref_far.keys).all() and (vals == ref_far.vals).all()
+    assert (eng.read_ranges() == ref_far.ranges).all()
+    assert np.abs(img.astype(np.int32) - ref_far.rgba.astype(np.int32)).max() <= 1
+    # and the near view itself, now that the buffers have grown
+    eng.raster_frame(near)
+    img = eng.draw()
+    keys, vals = eng.read_sorted()
+    assert (keys == ref_near.keys).all() and (vals == ref_near.vals).all()
+    assert np.abs(img.astype(np.int32) - ref_near.rgba.astype(np.int32)).max() <= 1
+    eng.close()
+
+
+def test_reserve_pairs_keeps_the_newest_frame_readable(E, oracle):
+    """tpdcu_reserve_pairs re-allocates the pair buffers: the newest frame is rendered again so that read_* still describe it."""
+    from torpedo_b200 import scenes
+    from torpedo_b200._lib import check, tpdcu
+    w, h = 256, 144
+    g = scenes.garden(20000, seed=72, log_scale_mean=-3.6)
+    scene = E.Scene()
+    scene.add_group(g)
+    cam = E.PerspectiveCamera(w, h)
+    cam.look_at((2.8, 2.8, 2.6), (0, 0, 0), (0, 0, 1))
+    ref = oracle.render(g, cam.pack(), w, h, 3)
+    eng = E.GaussianEngine(w, h)
+    eng.compile(scene)
+    eng.raster_frame(cam)
+    eng.finish()
+    check(tpdcu().tpdcu_reserve_pairs(eng._ctx, eng.capacity() * 4))
+    keys, vals = eng.read_sorted()
+    assert (keys == ref.keys).all() and (vals == ref.vals).all()
+    assert (eng.read_ranges() == ref.ranges).all()
+    assert np.abs(eng.draw().astype(np.int32) - ref.rgba.astype(np.int32)).max() <= 1
+    eng.close()
+
+
+@pytest.mark.parametrize("name,deg", [("sh3_binary", 3), ("sh2_shuffled", 2), ("sh1_mixed_types", 1)])
+def test_ply_file_to_rendered_frame(E, oracle, name, deg):
+    """PLY ingest to pixels: GaussianPoint::fromModel (the drop-in's reader, held bit-exact to the reference's by
+    tests/test_host_layer.py) -> Scene -> compile -> rasterFrame -> draw, against the oracle fed with the records the
+    REFERENCE's fromModel produced for the same file (tests/golden/ply/<name>.ref.npy)."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ply")
+    g = E.from_model(os.path.join(here, name + ".ply"))
+    want = np.load(os.path.join(here, name + ".ref.npy"))
+    assert (g.view(np.uint32) == want.view(np.uint32)).all()
+    w, h = 320, 200
+    cam = E.PerspectiveCamera(w, h)
+    cam.look_at((0.0, -6.0, 1.5), (0, 0, 0), (0, 0, 1))
+    scene = E.Scene()
+    scene.add_group(g)
+    eng = E.GaussianEngine(w, h)
+    eng.compile(scene, E.Settings(deg))
+    eng.raster_frame(cam)
+    img = eng.draw()
+    ref = oracle.render(want, cam.pack(), w, h, deg)
+    assert ref.pairs > 0
+    assert_frame_parity(eng, img, ref, len(g))
+    eng.close()

@@ -520,9 +520,11 @@ static int raster_one(tpdcu_ctx* c, const float* ubo, uint32_t sh_degree, cudaSt
     return TPDCU_OK;
 }
 
-// Host-side check of everything enqueued since the last check: wait for the frames, and render again (after growing the
-// buffers) those that overflowed — unless a later frame went to the same target, in which case the
-// frame has been superseded and repeating it would clobber the newer image.
+// Host-side check of everything enqueued since the last check: wait for the frames; if one overflowed its pair buffers,
+// grow them and render that frame AND EVERY LATER ONE again, in their original order — unless a later frame went to the same
+// target, in which case the frame has been superseded and repeating it would clobber the newer image. Repeating the later
+// frames too keeps two promises: the newest frame stays the newest (finish / read_* / introspection refer to it), and its
+// intermediate buffers are the ones of the (possibly re-allocated) slot it last ran on.
 static int finish_internal(tpdcu_ctx* c) {
     if (!c->have_newest) return fail(TPDCU_ERR_STATE, "no frame has been rendered");
     for (int attempt = 0; !c->unchecked.empty(); ++attempt) {
@@ -532,14 +534,17 @@ static int finish_internal(tpdcu_ctx* c) {
         pending.swap(c->unchecked);
         std::vector<FrameTicket> redo;
         uint32_t max_pairs = 0;
+        size_t first_overflow = pending.size();
         for (size_t i = 0; i < pending.size(); ++i) {
-            const FrameTicket& tk = pending[i];
-            const FrameStatus& st = c->status[tk.status];
-            if (st.pairs_total <= tk.ran_capacity) continue;
+            const FrameStatus& st = c->status[pending[i].status];
+            if (st.pairs_total <= pending[i].ran_capacity) continue;
             max_pairs = std::max(max_pairs, st.pairs_total);
+            first_overflow = std::min(first_overflow, i);
+        }
+        for (size_t i = first_overflow; i < pending.size(); ++i) {
             bool superseded = false;
-            for (size_t j = i + 1; j < pending.size() && !superseded; ++j) superseded = pending[j].out == tk.out;
-            if (!superseded) redo.push_back(tk);
+            for (size_t j = i + 1; j < pending.size() && !superseded; ++j) superseded = pending[j].out == pending[i].out;
+            if (!superseded) redo.push_back(pending[i]);
         }
         if (max_pairs)
             for (int k = 0; k < MAX_SLOTS; ++k)
@@ -548,6 +553,7 @@ static int finish_internal(tpdcu_ctx* c) {
         c->frames_repeated += (uint32_t)redo.size();
         for (const FrameTicket& tk : redo) {
             CK(cudaStreamSynchronize(tk.user_stream));
+            c->next_slot = tk.slot;  // every slot is idle here: the frame runs again where it ran (its internal target lives there)
             if (int r = raster_one(c, tk.ubo, tk.sh_degree, tk.user_stream, tk.out, tk.pitch)) return r;
         }
     }
@@ -1006,10 +1012,20 @@ int tpdcu_get_capacity(tpdcu_ctx* c, uint32_t* capacity_pairs) {
 
 int tpdcu_reserve_pairs(tpdcu_ctx* c, uint32_t capacity_pairs) {
     if (int r = check_ready(c)) return r;
+    if (c->have_newest)
+        if (int r = finish_internal(c)) return r;
     if (int r = sync_slots(c)) return r;
     CK(cudaDeviceSynchronize());
+    const bool regrow_newest = c->have_newest && capacity_pairs > c->slots[c->newest.slot].capacity;
     for (int k = 0; k < c->frames_in_flight; ++k)
         if (int r = ensure_pairs(c->slots[k], capacity_pairs)) return r;
+    if (regrow_newest) {
+        // the newest frame's pair buffers have just been replaced: render it again so that introspection still describes it
+        const FrameTicket tk = c->newest;
+        c->next_slot = tk.slot;
+        if (int r = raster_one(c, tk.ubo, tk.sh_degree, tk.user_stream, tk.out, tk.pitch)) return r;
+        if (int r = finish_internal(c)) return r;
+    }
     return TPDCU_OK;
 }
 
