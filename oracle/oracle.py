@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
         _lib.tpdo_from_model_fields.restype = None
         _lib.tpdo_from_model_fields.argtypes = [vp, u32, vp]
         _lib.tpdo_num_threads.restype = C.c_int
+        _lib.tpdo_set_num_threads.restype = None
+        _lib.tpdo_set_num_threads.argtypes = [C.c_int]
     return _lib
 
 
@@ -77,6 +79,16 @@ def radix_pass_count(width: int, height: int) -> int:
 
 def num_threads() -> int:
     return int(lib().tpdo_num_threads())
+
+
+def use_all_cores() -> int:
+    """Make the oracle use every core this process may run on (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    lib().tpdo_set_num_threads(cores)
+    return num_threads()
 
 
 @dataclass

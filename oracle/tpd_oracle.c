@@ -503,3 +503,12 @@ int tpdo_num_threads(void) {
     return 1;
 #endif
 }
+
+/* bench.py's reference arm under torchrun inherits OMP_NUM_THREADS=1: it asks for every core it may run on instead */
+void tpdo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -88,6 +88,8 @@ uint32_t tpdo_frame(const float* gaussians, uint32_t n, const uint32_t* entity_i
 void tpdo_from_model_fields(const float* raw59, uint32_t n, float* gaussians);
 
 int tpdo_num_threads(void);
+/* OpenMP threads of the following calls (bench.py's reference arm: all cores, whatever OMP_NUM_THREADS torchrun exported) */
+void tpdo_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

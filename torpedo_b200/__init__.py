@@ -6,6 +6,13 @@ Product layers:
   torpedo_b200/{_lib,engine}.py            ctypes mirror of the same interface (tests, bench)
 There is no CPU fallback: importing works anywhere, but every call needs the built library and an sm_100 GPU.
 """
-from .engine import Camera, GaussianEngine, PerspectiveCamera, Scene, Settings, TpdError  # noqa: F401
-
 __all__ = ["Camera", "GaussianEngine", "PerspectiveCamera", "Scene", "Settings", "TpdError"]
+
+
+def __getattr__(name):
+    # resolved on first use: `import torpedo_b200.scenes` (pure numpy input generators, also used by the benchmark's CPU
+    # reference arm) must not pull in the ctypes bindings of the native libraries
+    if name in __all__:
+        from . import engine
+        return getattr(engine, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -14,6 +14,13 @@ import torch
 import torch.distributed as dist
 
 
+def _world_rank() -> tuple[int, int]:
+    """(world, rank) of the default process group; a single process without one is world 1."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
 def views_of_rank(n_views: int, rank: int, world: int) -> list[int]:
     """Round-robin ownership: rank r renders views r, r + world, r + 2*world, ..."""
     if world < 1 or not (0 <= rank < world):
@@ -28,67 +35,72 @@ def owner_of_view(view: int, world: int) -> tuple[int, int]:
 
 def broadcast_scene(records: torch.Tensor | None, n: int, device: torch.device, src: int = 0) -> torch.Tensor:
     """Replicate the (n, 60) float32 GaussianPoint records from `src` to every rank (one collective, once per scene)."""
+    world, rank = _world_rank()
     buf = torch.empty((n, 60), dtype=torch.float32, device=device)
-    if dist.get_rank() == src:
+    if rank == src:
         if records is None or tuple(records.shape) != (n, 60):
             raise ValueError("source rank must provide the (n, 60) records")
         buf.copy_(records)
-    dist.broadcast(buf, src=src)
+    if world > 1:
+        dist.broadcast(buf, src=src)
     return buf
 
 
 def gather_frames(local_frames: torch.Tensor, n_views: int, dst: int = 0) -> torch.Tensor | None:
-    """Collect the per-rank frame batches on `dst` and put them back in view order.
+    """Collect the per-rank frame batches on `dst`, in view order.
 
     local_frames: (slots, H, W, 4) uint8 with slots = ceil(n_views / world) on EVERY rank (ranks that own one view fewer
-    leave their last slot unused) so that one fixed-size gather suffices. Returns (n_views, H, W, 4) on dst, None elsewhere.
+    leave their last slot unused) so that fixed-size gathers suffice. Returns (n_views, H, W, 4) on dst, None elsewhere.
     """
-    world, rank = dist.get_world_size(), dist.get_rank()
+    return _gather_slots(local_frames, n_views, dst, 0, local_frames.shape[0], None)
+
+
+def _gather_slots(local_frames, n_views, dst, s0, s1, out, pending=None):
+    """Gather slots [s0, s1) straight into view order: view v = slot * world + owner, so the frame rank r holds in slot s
+    belongs at out[s * world + r] and one gather per slot with that list of destinations needs no re-ordering copy
+    afterwards (a gather of whole per-rank batches followed by 64 device copies on `dst` cost a third of the 8-GPU batch).
+    With `pending` the gathers are started asynchronously and appended to it."""
+    world, rank = _world_rank()
     slots = -(-n_views // world)
     if local_frames.shape[0] != slots:
         raise ValueError(f"every rank must pass {slots} slots, got {local_frames.shape[0]}")
     if world == 1:
         return local_frames[:n_views]
-    parts = [torch.empty_like(local_frames) for _ in range(world)] if rank == dst else None
-    dist.gather(local_frames, parts, dst=dst)
-    if rank != dst:
-        return None
-    out = torch.empty((n_views,) + tuple(local_frames.shape[1:]), dtype=local_frames.dtype, device=local_frames.device)
-    for v in range(n_views):
-        r, s = owner_of_view(v, world)
-        out[v] = parts[r][s]
+    if out is None and rank == dst:
+        out = torch.empty((slots * world,) + tuple(local_frames.shape[1:]), dtype=local_frames.dtype, device=local_frames.device)
+    for s in range(s0, s1):
+        dests = [out[s * world + r] for r in range(world)] if rank == dst else None
+        work = dist.gather(local_frames[s], dests, dst=dst, async_op=pending is not None)
+        if pending is not None:
+            pending.append(work)
     return out
 
 
 def render_views(render_batch: Callable[[Sequence[int], torch.Tensor], None], n_views: int, height: int, width: int,
                  device: torch.device, dst: int = 0, chunk: int = 0) -> torch.Tensor | None:
     """Shard `n_views` over the ranks, let `render_batch(view_ids, out)` fill this rank's slots (out[k] <- view_ids[k]),
-    then gather. `render_batch` is the only place pixels are produced (GaussianEngine.raster_views on the GPU box).
+    and gather the frames on `dst` in view order. `render_batch` is the only place pixels are produced (the GaussianEngine
+    on the GPU box); it may return before the frames are finished as long as the work is ordered on the current stream.
 
-    chunk > 0: render `chunk` slots at a time and start the gather of each chunk asynchronously, so that the transfer of
+    chunk > 0: render `chunk` slots at a time and start the gathers of each chunk asynchronously, so that the transfer of
     one chunk overlaps the rendering of the next; the result is the same tensor."""
-    world, rank = dist.get_world_size(), dist.get_rank()
+    world, rank = _world_rank()
     mine = views_of_rank(n_views, rank, world)
     slots = -(-n_views // world)
     local = torch.zeros((slots, height, width, 4), dtype=torch.uint8, device=device)
-    if chunk <= 0 or world == 1:
+    if world == 1:
         if mine:
             render_batch(mine, local[: len(mine)])
-        return gather_frames(local, n_views, dst)
-    parts = [torch.empty_like(local) for _ in range(world)] if rank == dst else None
-    pending = []
-    for s0 in range(0, slots, chunk):
-        s1 = min(s0 + chunk, slots)
+        return local[:n_views]
+    step = chunk if chunk > 0 else max(slots, 1)
+    out = None
+    pending = [] if chunk > 0 else None
+    for s0 in range(0, slots, step):
+        s1 = min(s0 + step, slots)
         ids = mine[s0:s1]
         if ids:
             render_batch(ids, local[s0:s0 + len(ids)])
-        pending.append(dist.gather(local[s0:s1], [p[s0:s1] for p in parts] if rank == dst else None, dst=dst, async_op=True))
-    for work in pending:
+        out = _gather_slots(local, n_views, dst, s0, s1, out, pending)
+    for work in pending or []:
         work.wait()
-    if rank != dst:
-        return None
-    out = torch.empty((n_views,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    for v in range(n_views):
-        r, s = owner_of_view(v, world)
-        out[v] = parts[r][s]
-    return out
+    return out[:n_views] if rank == dst else None
