@@ -127,6 +127,12 @@ int tpdcu_read_ranges(tpdcu_ctx* ctx, uint32_t* host_ranges2, uint32_t tile_coun
  * offset). The frame never materialises them — its duplication stage runs over the depth-sorted Gaussians — so this
  * call rebuilds them from the last frame's per-Gaussian records, in the reference's order. */
 int tpdcu_read_unsorted(tpdcu_ctx* ctx, uint64_t* host_keys, uint32_t* host_vals, uint32_t count);
+/* What the duplication stage (emit_kernel, the stage that replaces keygen.slang:21-53) REALLY wrote for the newest frame: the
+ * first `count` pair words (tile << extra | top depth bits) << 32 | Gaussian index, in depth order of the Gaussians and
+ * row-major tile order within a Gaussian (`extra` = tile_bits reported by tpdcu_get_sort_info minus ceil(log2(tiles))).
+ * The tile sort consumes that buffer, so the call renders the frame again up to the duplication stage, copies the words
+ * and then renders it once more in full; parity tests use it to check the real emission, not a rebuilt one. */
+int tpdcu_read_emitted(tpdcu_ctx* ctx, uint64_t* host_words, uint32_t count);
 /* When enabled, CUDA events bracket every stage of each frame. times_ms (last finished frame):
  * [0] clear+camera setup [1] preprocess (projection, scan, visible compaction) + SH colour [2] depth sort of the visible
  * Gaussians [3] duplication [4] tile sort of the pairs [5] ranges [6] blend [7] whole frame

@@ -1,5 +1,5 @@
 """Per-source-line instruction and stall-sample shares of an .ncu-rep captured with --import-source on.
-python profiles/ncu_lines.py <report> [top N]"""
+python profiles/ncu_lines.py <report> [top N] [launch index within the report; default: all launches together]"""
 import collections
 import csv
 import io
@@ -8,16 +8,24 @@ import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+want = int(sys.argv[3]) if len(sys.argv) > 3 else None
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 cur, hdr = None, None
+first_file, launch = None, -1
 agg = collections.defaultdict(lambda: [0, 0, "", 0])
 for r in rows:
     if len(r) == 2 and r[0] == "File Path":
         cur = r[1].split("/")[-1]
+        if first_file is None:
+            first_file = r[1]
+        if r[1] == first_file:
+            launch += 1   # the per-file blocks of every launch start over with the same file
         continue
     if r and r[0] == "Line No":
         hdr = r
+        continue
+    if want is not None and launch != want:
         continue
     if hdr and len(r) == len(hdr) and r[0].isdigit():
         try:

@@ -40,6 +40,7 @@ TPDCU_SYMBOLS = {
     "tpdcu_read_values": (i32, [vp, vp, u32]),
     "tpdcu_read_ranges": (i32, [vp, vp, u32]),
     "tpdcu_read_unsorted": (i32, [vp, vp, vp, u32]),
+    "tpdcu_read_emitted": (i32, [vp, vp, u32]),
     "tpdcu_enable_stage_timing": (i32, [vp, i32]),
     "tpdcu_stage_times_ms": (i32, [vp, vp]),
     "tpdcu_get_sort_info": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),

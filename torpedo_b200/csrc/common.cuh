@@ -18,8 +18,15 @@ constexpr uint32_t SH_PLANES = 12;        // 48 SH floats = 12 float4 per Gaussi
 constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
+#ifndef TPDCU_SORT_WS
+#define TPDCU_SORT_WS 0                  // 1: the frame's sorts run the warp-specialised persistent pass (sort.cu; measured, slower)
+#endif
 #ifndef TPDCU_SORT_KPT
+#if TPDCU_SORT_WS
+#define TPDCU_SORT_KPT 24                // 6144-key tiles: two groups x two 48 KB key buffers per SM
+#else
 #define TPDCU_SORT_KPT 32
+#endif
 #endif
 #ifndef TPDCU_SORT_MINB
 #define TPDCU_SORT_MINB 2

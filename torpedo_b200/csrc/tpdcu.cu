@@ -153,6 +153,7 @@ struct tpdcu_ctx {
     uint32_t frames_repeated = 0;        // frames rendered again because they overflowed (grow-only buffers: warm-up only)
 
     bool timing = false;
+    bool stop_after_emit = false;        // introspection (tpdcu_read_emitted): frames end after the duplication stage
     cudaEvent_t ev[9] = {};
     float stage_ms[TPDCU_NUM_STAGES] = {};
 
@@ -324,7 +325,7 @@ struct FrameLaunch {
 
 // The part of a frame whose launch parameters do not change from frame to frame: everything between the camera setup and
 // the blend. Either enqueued directly or captured once into a CUDA graph and replayed.
-static int enqueue_middle(tpdcu_ctx* c, FrameSlot& f, const FrameLaunch& l, cudaStream_t s, bool timing) {
+static int enqueue_middle(tpdcu_ctx* c, FrameSlot& f, const FrameLaunch& l, cudaStream_t s, bool timing, bool stop_after_emit = false) {
     CK(cudaMemsetAsync(f.zero_region, 0, l.zero_bytes, s));
     if (timing) CK(cudaEventRecord(c->ev[1], s));
     CK(launch_preprocess(l.pre, s));   // the SH colour is evaluated by the blend, for the splats it stages
@@ -333,6 +334,7 @@ static int enqueue_middle(tpdcu_ctx* c, FrameSlot& f, const FrameLaunch& l, cuda
     if (timing) CK(cudaEventRecord(c->ev[3], s));
     CK(launch_emit(l.emit, s));
     if (timing) CK(cudaEventRecord(c->ev[4], s));
+    if (stop_after_emit) return TPDCU_OK;  // tpdcu_read_emitted: the pair words as the duplication stage left them
     CK(launch_sort(l.tile_sort, 0, s, timing ? c->ev[8] : nullptr));
     if (timing) CK(cudaEventRecord(c->ev[5], s));
     CK(launch_ranges(l.raster, f.capacity, s));
@@ -407,7 +409,8 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     CK(launch_setup(p, cu, s));
 
     bool replayed = false;
-    if (c->use_graph && !t) {
+    const bool stop = c->stop_after_emit;
+    if (c->use_graph && !t && !stop) {
         GraphSig sig;
         memset(&sig, 0, sizeof(sig));
         sig.zero_region = f.zero_region; sig.zero_bytes = l.zero_bytes; sig.keys0 = f.keys[0]; sig.keys1 = f.keys[1];
@@ -442,9 +445,9 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
         }
     }
     if (!replayed)
-        if (int r = enqueue_middle(c, f, l, s, t)) return r;
+        if (int r = enqueue_middle(c, f, l, s, t, stop)) return r;
 
-    if (!t) {
+    if (!t && !stop) {
         if (tk.out == f.target) {
             // the slot's own target: the only other user is an asynchronous read of the frame it held before
             // (tpdcu_read_frame_async); the blend does not have to wait for the newer frames' copies on the caller's stream
@@ -455,7 +458,7 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
             CK(cudaStreamWaitEvent(s, f.fork, 0));
         }
     }
-    CK(launch_blend(ra, s));
+    if (!stop) CK(launch_blend(ra, s));
     if (t) CK(cudaEventRecord(c->ev[7], s));
 
     FrameStatus* st = &c->status[tk.status];
@@ -945,6 +948,33 @@ int tpdcu_read_unsorted(tpdcu_ctx* c, uint64_t* host_keys, uint32_t* host_vals, 
     cudaFree(dv);
     if (e != cudaSuccess) return fail(TPDCU_ERR_CUDA, std::string("read_unsorted: ") + cudaGetErrorString(e));
     return TPDCU_OK;
+}
+
+int tpdcu_read_emitted(tpdcu_ctx* c, uint64_t* host_words, uint32_t count) {
+    if (int r = check_ready(c)) return r;
+    if (!host_words && count) return fail(TPDCU_ERR_INVALID, "host buffer is null");
+    if (int r = finish_internal(c)) return r;
+    if (count > last_status(c).pairs_total) return fail(TPDCU_ERR_INVALID, "count exceeds the frame's pair count");
+    // The tile sort ping-pongs over the buffer the duplication stage wrote, so its output is gone when a frame ends: run the
+    // newest frame again on its slot up to and including emit_kernel, copy the words, then render it once more in full so
+    // that every other read still describes a complete frame.
+    const FrameTicket tk = c->newest;
+    c->stop_after_emit = true;
+    c->next_slot = tk.slot;
+    int rc = raster_one(c, tk.ubo, tk.sh_degree, tk.user_stream, tk.out, tk.pitch);
+    c->stop_after_emit = false;
+    if (rc == TPDCU_OK) rc = finish_internal(c);
+    if (rc == TPDCU_OK && count) {
+        FrameSlot& f = c->slots[tk.slot];
+        cudaError_t e = cudaMemcpyAsync(host_words, f.keys[0], (size_t)count * 8, cudaMemcpyDeviceToHost, f.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(f.stream);
+        if (e != cudaSuccess) rc = fail(TPDCU_ERR_CUDA, std::string("read_emitted: ") + cudaGetErrorString(e));
+    }
+    c->next_slot = tk.slot;
+    const int rc2 = raster_one(c, tk.ubo, tk.sh_degree, tk.user_stream, tk.out, tk.pitch);
+    if (rc == TPDCU_OK) rc = rc2;
+    if (rc == TPDCU_OK) rc = finish_internal(c);
+    return rc;
 }
 
 int tpdcu_enable_stage_timing(tpdcu_ctx* c, int enable) {

@@ -297,6 +297,14 @@ class GaussianEngine:
             check(tpdcu().tpdcu_read_unsorted(self._ctx, _ptr(keys), _ptr(vals), p))
         return keys, vals
 
+    def read_emitted(self) -> np.ndarray:
+        """The pair words emit_kernel wrote for the newest frame (tpdcu_read_emitted), before the tile sort."""
+        p = self.counts()[0]
+        words = np.zeros(p, dtype=np.uint64)
+        if p:
+            check(tpdcu().tpdcu_read_emitted(self._ctx, _ptr(words), p))
+        return words
+
     def read_ranges(self) -> np.ndarray:
         tiles = ((self.width + 15) // 16) * ((self.height + 15) // 16)
         out = np.zeros((tiles, 2), dtype=np.uint32)
