@@ -18,15 +18,8 @@ constexpr uint32_t SH_PLANES = 12;        // 48 SH floats = 12 float4 per Gaussi
 constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
-#ifndef TPDCU_SORT_WS
-#define TPDCU_SORT_WS 0                  // 1: the frame's sorts run the warp-specialised persistent pass (sort.cu; measured, slower)
-#endif
 #ifndef TPDCU_SORT_KPT
-#if TPDCU_SORT_WS
-#define TPDCU_SORT_KPT 24                // 6144-key tiles: two groups x two 48 KB key buffers per SM
-#else
 #define TPDCU_SORT_KPT 32
-#endif
 #endif
 #ifndef TPDCU_SORT_MINB
 #define TPDCU_SORT_MINB 2
@@ -41,12 +34,28 @@ constexpr uint32_t SORT_TILE_PAIRS = SORT_THREADS * SORT_KPT_PAIRS;
 constexpr uint32_t SORT_TILE = SORT_TILE_WORDS > SORT_TILE_PAIRS ? SORT_TILE_WORDS : SORT_TILE_PAIRS;  // buffer granularity
 constexpr uint32_t SORT_WARPS = SORT_THREADS / 32;
 
+// Look-back chains of a pass (sort.cu): the input of a pass is cut into SORT_CHAINS contiguous segments whose digit
+// histograms are known up front, so every segment runs its own, eight times shorter, decoupled look-back. Segments of the
+// first pass are equal ranges of positions; segments of pass p > 0 are the runs of 256 / SORT_CHAINS consecutive bins that
+// pass p - 1 wrote (so a key's segment is a function of its previous digit and the histogram kernel can count it).
+#ifndef TPDCU_SORT_CHAINS
+#define TPDCU_SORT_CHAINS 8
+#endif
+constexpr uint32_t SORT_CHAINS = TPDCU_SORT_CHAINS;                    // words sorts; the standalone pair sort runs one chain
+constexpr uint32_t SORT_CHAIN_BINS = SORT_BINS / SORT_CHAINS;          // previous-pass bins per segment
+constexpr uint32_t SORT_WORD_PASSES = 4;                               // words sorts order at most 32 key bits
+constexpr uint32_t SORT_CHAIN_ROWS = SORT_WORD_PASSES * SORT_CHAINS > SORT_MAX_PASSES ? SORT_WORD_PASSES * SORT_CHAINS : SORT_MAX_PASSES;
+static_assert((SORT_CHAINS & (SORT_CHAINS - 1)) == 0 && SORT_CHAINS <= 32, "SORT_CHAINS is a power of two");
+
 // Tickets and digit histograms of one radix sort.
 struct SortCtl {
     uint32_t hist_done;                   // histogram CTAs that have added their counts (the last one makes the plan)
     uint32_t pad[3];
     uint32_t ticket[SORT_MAX_PASSES];
-    uint32_t hist[SORT_MAX_PASSES][SORT_BINS];  // global digit histograms (then exclusive offsets)
+    uint32_t hist[SORT_MAX_PASSES][SORT_BINS];  // exclusive digit offsets of every pass (made by the plan)
+    // row pass * chains + c: keys of segment c per digit of that pass (histogram kernel); the plan turns a pass's rows into
+    // the exclusive sum over the segments before c: the offset of segment c's first key inside every bin's output run
+    uint32_t chain_hist[SORT_CHAIN_ROWS][SORT_BINS];
 };
 
 // Per-frame control block; lives at the head of the per-frame zeroed region.
@@ -92,6 +101,9 @@ struct SortPlan {
     uint32_t pad;
     uint32_t skip[SORT_MAX_PASSES];       // pass is an identity permutation (single occupied bin)
     uint32_t src_sel[SORT_MAX_PASSES];    // ping-pong buffer the pass reads from
+    uint32_t chains;                      // look-back chains per pass: SORT_CHAINS (words) or 1 (pairs)
+    uint32_t seg_start[SORT_MAX_PASSES][SORT_CHAINS + 1];   // first input position of every segment of the pass (+ n)
+    uint32_t seg_tiles[SORT_MAX_PASSES][SORT_CHAINS + 1];   // tiles of the segments before c: descriptor row of its tile 0 (+ total)
 };
 
 // Camera-derived constants, produced once per frame by the setup kernel.

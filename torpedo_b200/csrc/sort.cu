@@ -26,29 +26,28 @@ constexpr uint32_t LOOKBACK_VALUE_MASK = (1u << 30) - 1u;
 #define TPDCU_LOOKBACK_BATCH 8
 #endif
 constexpr uint32_t LOOKBACK_BATCH = TPDCU_LOOKBACK_BATCH;
-#ifndef TPDCU_SORT_PREFETCH_TILES
-#define TPDCU_SORT_PREFETCH_TILES 296
+#ifndef TPDCU_HIST_CTAS_TILE
+#define TPDCU_HIST_CTAS_TILE 2           // histogram CTAs per SM (each adds passes x segments x 256 counters to the global ones)
 #endif
-#ifndef TPDCU_SORT_RANK_ATOMS
-#define TPDCU_SORT_RANK_ATOMS 1
+#ifndef TPDCU_HIST_CTAS_DEPTH
+#define TPDCU_HIST_CTAS_DEPTH 1
 #endif
 #ifndef TPDCU_SORT_SWIZZLE
-#define TPDCU_SORT_SWIZZLE 1
+#define TPDCU_SORT_SWIZZLE 1             // bank swizzle of the per-warp digit counters (hist_slot)
 #endif
-#ifndef TPDCU_SORT_LOOKBACK_VEC
-#define TPDCU_SORT_LOOKBACK_VEC 0        // per-tile kernel: 64 threads walk four bins each with 16-byte descriptor loads
+#ifndef TPDCU_SORT_GRID_FACTOR
+#define TPDCU_SORT_GRID_FACTOR 1         // CTAs launched per resident slot of the persistent pass kernel
 #endif
-#ifndef TPDCU_SORT_LOOKBACK_EARLY
-#define TPDCU_SORT_LOOKBACK_EARLY 0
+#ifndef TPDCU_SORT_DRAW_EARLY
+#define TPDCU_SORT_DRAW_EARLY 1          // 1: the next ticket is drawn before the ranking instead of after it
 #endif
 #ifndef TPDCU_SORT_RANK_BATCH
-#define TPDCU_SORT_RANK_BATCH 8
+#define TPDCU_SORT_RANK_BATCH 8          // ranking atomics in flight per thread before their keys are scattered
 #endif
 constexpr uint32_t SORT_RANK_BATCH = TPDCU_SORT_RANK_BATCH;
 #ifndef TPDCU_SORT_MINB_WORDS
 #define TPDCU_SORT_MINB_WORDS 2
 #endif
-constexpr uint32_t SORT_PREFETCH_TILES = TPDCU_SORT_PREFETCH_TILES;  // 148 SMs x 3 resident CTAs
 
 // What a sort launch works on (see SORT_KIND_* in common.cuh); derived on the device because n and the depth range are.
 struct SortSpec {
@@ -105,20 +104,37 @@ __host__ __device__ __forceinline__ uint32_t passes_needed(uint32_t total_bits) 
 __device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, SortPlan* plan, uint32_t kind, uint32_t n_host,
                                           uint32_t capacity, uint32_t end_bit, uint32_t tile_bits);
 
+__host__ __device__ __forceinline__ uint32_t chains_of(uint32_t kind) { return kind == SORT_KIND_PAIRS ? 1u : SORT_CHAINS; }
+__host__ __device__ __forceinline__ uint32_t tile_of(uint32_t kind) { return kind == SORT_KIND_PAIRS ? SORT_TILE_PAIRS : SORT_TILE_WORDS; }
+// length of a first-pass segment: whole tiles, SORT_CHAINS segments cover n
+__device__ __forceinline__ uint32_t first_pass_segment(uint32_t n, uint32_t kind) {
+    const uint32_t tile = tile_of(kind), chains = chains_of(kind);
+    const uint32_t tiles = (n + tile - 1) / tile;
+    return max((tiles + chains - 1) / chains, 1u) * tile;
+}
+
+// Every CTA counts a contiguous slice of the keys: for every pass p and every segment c of that pass's input (see
+// SORT_CHAINS in common.cuh) the digit histogram of the keys that belong to it. Segment of a key: its position / segment
+// length for the first pass, its previous digit / SORT_CHAIN_BINS for the later ones.
 template <bool WORDS>
 __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t* __restrict__ keys, const FrameCtl* frame, SortCtl* ctl,
                                                                   SortPlan* plan, uint32_t kind, uint32_t n_host, uint32_t capacity,
                                                                   uint32_t end_bit, uint32_t tile_bits) {
-    __shared__ uint32_t h[SORT_MAX_PASSES][SORT_BINS];
+    __shared__ uint32_t h[SORT_CHAIN_ROWS * SORT_BINS];
     const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit, tile_bits);
     const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
-    for (uint32_t k = threadIdx.x; k < num_passes * SORT_BINS; k += HIST_THREADS) (&h[0][0])[k] = 0;
+    const uint32_t chains = chains_of(kind), rows = num_passes * chains;
+    const uint32_t seg0 = first_pass_segment(n, kind);
+    for (uint32_t k = threadIdx.x; k < rows * SORT_BINS; k += HIST_THREADS) h[k] = 0;
     __syncthreads();
     // Each thread takes HIST_KPT CONSECUTIVE elements (two 32-byte loads): the pairs of one Gaussian are adjacent in the
     // unsorted buffer and usually share the upper tile bits, so run-length encoding the digits in registers removes most
     // shared-memory atomics and nearly all same-address conflicts.
     const uint32_t chunk = HIST_THREADS * HIST_KPT;
-    for (uint32_t base = blockIdx.x * chunk; base < n; base += gridDim.x * chunk) {
+    const uint32_t chunks = (n + chunk - 1) / chunk, per_cta = (chunks + gridDim.x - 1) / gridDim.x;
+    const uint32_t slice_end = min((uint64_t)n, (uint64_t)(blockIdx.x + 1) * per_cta * chunk);
+    for (uint64_t base64 = (uint64_t)blockIdx.x * per_cta * chunk; base64 < slice_end; base64 += chunk) {
+        const uint32_t base = (uint32_t)base64;
         const uint32_t first = base + threadIdx.x * HIST_KPT;
         uint64_t k[HIST_KPT];
         if (first + HIST_KPT <= n) {
@@ -136,32 +152,42 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
         if (valid) {
 #pragma unroll
             for (uint32_t j = 0; j < HIST_KPT; ++j) k[j] = sort_key<WORDS>(k[j], sp.bias);
+            // first-pass segment of the thread's elements: changes at most once inside its HIST_KPT consecutive positions
+            const uint32_t c_first = first / seg0;
+            const uint32_t c_change = (c_first + 1u) * seg0 - first;   // elements j >= c_change sit in the next segment
             for (uint32_t p = 0; p < num_passes; ++p) {
                 const uint32_t shift = p * SORT_RADIX_BITS, mask = pass_mask(p, sp.total_bits);
-                uint32_t run_digit = (uint32_t)(k[0] >> shift) & mask, run = 1;
+                const uint32_t prev_shift = (p - 1u) * SORT_RADIX_BITS, prev_mask = p ? pass_mask(p - 1u, sp.total_bits) : 0u;
+                auto slot = [&](uint32_t j) {
+                    const uint32_t d = (uint32_t)(k[j] >> shift) & mask;
+                    uint32_t c = 0;
+                    if (chains > 1) c = p == 0 ? c_first + (j >= c_change ? 1u : 0u) : ((uint32_t)(k[j] >> prev_shift) & prev_mask) / SORT_CHAIN_BINS;
+                    return (p * chains + c) * SORT_BINS + hist_slot(d);   // bank swizzle: the tile sort's low digits sit at stride 4
+                };
+                uint32_t run_slot = slot(0), run = 1;
 #pragma unroll
                 for (uint32_t j = 1; j < HIST_KPT; ++j) {
                     if (j < valid) {
-                        const uint32_t d = (uint32_t)(k[j] >> shift) & mask;
-                        if (d != run_digit) {
-                            atomicAdd(&h[p][run_digit], run);
-                            run_digit = d;
+                        const uint32_t sl = slot(j);
+                        if (sl != run_slot) {
+                            atomicAdd(&h[run_slot], run);
+                            run_slot = sl;
                             run = 0;
                         }
                         ++run;
                     }
                 }
-                atomicAdd(&h[p][run_digit], run);
+                atomicAdd(&h[run_slot], run);
             }
         }
     }
     __syncthreads();
-    for (uint32_t k = threadIdx.x; k < num_passes * SORT_BINS; k += HIST_THREADS) {
-        const uint32_t c = (&h[0][0])[k];
-        if (c) atomicAdd(&ctl->hist[0][0] + k, c);
+    for (uint32_t k = threadIdx.x; k < rows * SORT_BINS; k += HIST_THREADS) {
+        const uint32_t c = h[(k & ~(SORT_BINS - 1u)) | hist_slot(k & (SORT_BINS - 1u))];   // counter of bin k & 255 of row k >> 8
+        if (c) atomicAdd(&ctl->chain_hist[0][0] + k, c);
     }
-    // The last CTA to get here turns the histograms into the plan (exclusive digit offsets, passes to skip, ping-pong
-    // schedule): one launch and one kernel boundary less per sort than a plan kernel of its own.
+    // The last CTA to get here turns the histograms into the plan (exclusive digit offsets, segment offsets, passes to skip,
+    // ping-pong schedule): one launch and one kernel boundary less per sort than a plan kernel of its own.
     __shared__ uint32_t s_last;
     __threadfence();
     __syncthreads();
@@ -174,7 +200,7 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
 }
 
 // ---------------------------------------------------------------------------------------------------
-// plan: exclusive digit offsets, identity-pass detection, ping-pong schedule
+// plan: exclusive digit offsets, segment offsets, identity-pass detection, ping-pong schedule
 // ---------------------------------------------------------------------------------------------------
 
 // Runs in ONE CTA of at least SORT_BINS threads; every thread of the CTA must call it (block barriers inside), the first
@@ -185,12 +211,21 @@ __device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, S
     __shared__ uint32_t s_skip[SORT_MAX_PASSES];
     const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit, tile_bits);
     const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
+    const uint32_t chains = chains_of(kind);
     const uint32_t b = threadIdx.x, lane = b & 31u, warp = b >> 5;
     const bool owner = b < SORT_BINS;
     if (b < SORT_MAX_PASSES) s_skip[b] = 0;
     __syncthreads();
     for (uint32_t p = 0; p < num_passes; ++p) {
-        const uint32_t c = owner ? ld_relaxed_u32(&ctl->hist[p][b]) : 0u;
+        // per bin: the segments' counts become the exclusive sum over the segments before them; their total is the bin's count
+        uint32_t c = 0;
+        if (owner)
+            for (uint32_t ch = 0; ch < chains; ++ch) {
+                uint32_t* cell = &ctl->chain_hist[p * chains + ch][b];
+                const uint32_t v = ld_relaxed_u32(cell);
+                *cell = c;
+                c += v;
+            }
         if (owner && c == n) s_skip[p] = 1;  // every key falls in this bin (also true for n == 0)
         uint32_t incl = c;
 #pragma unroll
@@ -222,6 +257,22 @@ __device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, S
         plan->bias = sp.bias;
         plan->total_bits = sp.total_bits;
         plan->tile_shift = kind == SORT_KIND_TILE ? depth_split(frame, tile_bits).extra : 0u;
+        // segments of every pass's input and the descriptor rows of their tiles. A pass that follows an identity pass finds
+        // every key in one previous bin: one segment covers [0, n) and the others are empty, which is what its keys' counts say.
+        plan->chains = chains;
+        const uint32_t tile = tile_of(kind), seg0 = first_pass_segment(n, kind);
+        for (uint32_t p = 0; p < num_passes; ++p) {
+            uint32_t rows = 0;
+            for (uint32_t ch = 0; ch <= SORT_CHAINS; ++ch) {
+                uint32_t start = n;
+                if (ch < chains) start = p == 0 ? (uint32_t)min((uint64_t)n, (uint64_t)ch * seg0) : ctl->hist[p - 1][ch * (SORT_BINS / chains)];
+                plan->seg_start[p][ch] = start;
+            }
+            for (uint32_t ch = 0; ch <= SORT_CHAINS; ++ch) {
+                plan->seg_tiles[p][ch] = rows;
+                if (ch < SORT_CHAINS) rows += (plan->seg_start[p][ch + 1] - plan->seg_start[p][ch] + tile - 1) / tile;
+            }
+        }
     }
 }
 
@@ -261,17 +312,21 @@ struct OnesweepSmem {
     uint64_t keys[TILE];
     alignas(16) uint32_t warp_hist[SORT_WARPS][SORT_BINS];  // zeroed with 16-byte stores
     alignas(16) uint32_t global_base[SORT_BINS];
-    alignas(16) uint32_t bin_count[SORT_BINS];   // per bin: valid keys of this tile / tile-local offset of the bin's run
-    alignas(16) uint32_t bin_base[SORT_BINS];    // (handed from the thread == bin phase to the vectorised look-back)
     uint32_t scan[SORT_BINS / 32];
     uint32_t part;
     uint32_t vals[WITH_VALS ? TILE : 1];
 };
 static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phases");
 
-// One CTA = one tile of TILE elements. Phases (block barriers in between):
-//   ticket + zero per-warp histograms | load keys, early counts | per-bin: warp prefix, publish aggregate, bin scan |
-//   stable ranking (ballots) + scatter to smem | look-back per bin | coalesced write-out (+ value scatter / write-out)
+// A resident CTA works through tiles of TILE elements, one ticket at a time. Per tile (block barriers in between):
+//   digits + counting atomics (keys already in registers) | per bin: prefix over the warps, publish the aggregate, scan the
+//   bins | ranking atomics + scatter to smem | draw the NEXT ticket, issue the next tile's key loads | look-back per bin |
+//   coalesced write-out (+ value scatter / write-out) | next tile.
+// Between a CTA's end and its successor's first load lie a block launch, a ticket round trip and the plan loads — 2 us of a
+// 10 us tile life with one tile per CTA (per-tile trace, profiles/micro/ws_trace.cu); the loop pays them once per CTA, and
+// the next tile's keys travel while this tile's look-back and write-out run. The next ticket is drawn AFTER this tile's
+// ranking, i.e. at a fixed phase of every CTA's cycle: tickets are handed out in the order the tiles will really be
+// started, which keeps the look-back from waiting on a tile whose CTA is still busy with the previous one.
 template <int MODE>
 __global__ void __launch_bounds__(SORT_THREADS, MODE == MODE_WORDS ? TPDCU_SORT_MINB_WORDS : TPDCU_SORT_MINB)
 onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, SortCtl* ctl,
@@ -284,593 +339,152 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     if (plan->skip[pass]) return;
-    const uint32_t n = plan->n;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) sm.part = atomicAdd(&ctl->ticket[pass], 1u);
-    {
-        uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[0][0]);
+    // the pass's segments (look-back chains): fetched while the first ticket is on its way
+    uint32_t seg_start[SORT_CHAINS + 1], seg_tiles[SORT_CHAINS + 1];
 #pragma unroll
-        for (uint32_t k = 0; k < SORT_WARPS * SORT_BINS / 4 / SORT_THREADS; ++k) z[tid + k * SORT_THREADS] = make_uint4(0, 0, 0, 0);
+    for (uint32_t c = 0; c <= SORT_CHAINS; ++c) {
+        seg_start[c] = plan->seg_start[pass][c];
+        seg_tiles[c] = plan->seg_tiles[pass][c];
     }
-    __syncthreads();
-    const uint32_t part = sm.part;
-    const uint64_t tile_base64 = (uint64_t)part * SORT_TILE;
-    if (tile_base64 >= n) return;
-    if (tid == 0) WS_STAMP(part, 0);
-    const uint32_t tile_base = (uint32_t)tile_base64;
-    const uint32_t n_valid = min(SORT_TILE, n - tile_base);
-
+    const uint32_t chains = plan->chains;
+    const uint32_t total_tiles = seg_tiles[SORT_CHAINS];
     const uint32_t src = plan->src_sel[pass];
     const uint64_t* __restrict__ src_keys = src ? keys1 : keys0;
     const uint32_t* __restrict__ src_vals = src ? vals1 : vals0;
     uint64_t* __restrict__ dst_keys = src ? keys0 : keys1;
     uint32_t* __restrict__ dst_vals = src ? vals0 : vals1;
-
-    // Tiles run in ticket order; the tile SORT_PREFETCH_TILES tickets ahead starts roughly when this one retires. One TMA
-    // bulk prefetch per array pulls it into L2 now, so that its loads are L2 hits then.
-    if (tid == 0) {
-        const uint64_t ahead = (uint64_t)(part + SORT_PREFETCH_TILES) * SORT_TILE;
-        if (ahead + SORT_TILE <= n) {
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_keys + ahead), "r"((uint32_t)(SORT_TILE * sizeof(uint64_t))) : "memory");
-            if (IN_PAIRS)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_vals + ahead), "r"((uint32_t)(SORT_TILE * sizeof(uint32_t))) : "memory");
-        }
-    }
     const uint32_t bias = plan->bias, total_bits = plan->total_bits;
     const uint32_t shift = pass * SORT_RADIX_BITS, mask = pass_mask(pass, total_bits);
     auto digit_in = [&](uint64_t k) { return (uint32_t)(sort_key<WORDS>(k, bias) >> shift) & mask; };
     auto digit_out = digit_in;  // elements sit in shared memory in their input format
+    const uint32_t my_slot = hist_slot(tid);
+    const uint32_t hist_row = (uint32_t)__cvta_generic_to_shared(&sm.warp_hist[warp][0]);
 
-    // ---- load (warp-striped: item k of lane l sits at warp_base + 32k + l) --------------------------
-    uint64_t key[SORT_KPT];
-    const uint32_t warp_base = tile_base + warp * (32u * SORT_KPT) + lane;
-    const bool full = n_valid == SORT_TILE;
-    if (full) {
+    // Ticket -> (segment c, tile k of that segment), round-robin over the segments that still have tiles: consecutive tickets
+    // go to different chains, so a chain's consecutive tiles start SORT_CHAINS tickets apart and its look-back is that much
+    // shallower. F(k) = sum_c min(tiles_c, k) tickets precede round k; k is the last round that starts at or before the ticket.
+    struct TileId { uint32_t chain, k, begin, end, row0; };   // segment, tile of the segment, the segment's range and first row
+    auto locate = [&](uint32_t ticket) {
+        TileId t{ 0u, ticket, 0u, 0u, 0u };
+        if (chains > 1) {
+            auto before_round = [&](uint32_t k) {
+                uint32_t f = 0;
 #pragma unroll
-        for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = src_keys[warp_base + k * 32u];
-    } else {
+                for (uint32_t c = 0; c < SORT_CHAINS; ++c) f += min(seg_tiles[c + 1] - seg_tiles[c], k);
+                return f;
+            };
+            uint32_t lo = 0, hi = 0;
 #pragma unroll
-        for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = (warp_base + k * 32u) < n ? src_keys[warp_base + k * 32u] : ~0ull;  // padding sorts last
-    }
-
-    // ---- digits, computed once and packed four to a register; padding (only in the last tile) goes to the top bin -------
-    // What is packed is the digit's COUNTER SLOT, hist_slot(d) = d ^ ((d >> 5) & 3): the per-warp counters are only ever
-    // indexed by it. The tile sort's low digit is (tile & 63) << 2 | top depth bits, and neighbours in depth order share
-    // those depth bits, so the digits of a row sit at stride 4: unswizzled they fall on 8 of the 32 banks (ncu: 7.7
-    // wavefronts per ranking atomic, 5.6 per counting atomic). XOR-ing bits 5-6 into bits 0-1 spreads a stride-4 run over
-    // all banks and still maps 32 consecutive bins (a warp of the thread == bin phases) onto 32 distinct banks.
-    uint32_t dpack[SORT_KPT / 4];
+            for (uint32_t c = 0; c < SORT_CHAINS; ++c) hi = max(hi, seg_tiles[c + 1] - seg_tiles[c]);
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                if (before_round(mid) <= ticket) lo = mid;
+                else hi = mid - 1;
+            }
+            t.k = lo;
+            uint32_t idx = ticket - before_round(lo);   // idx-th segment, in order, that has a tile k
+            bool found = false;
 #pragma unroll
-    for (uint32_t q = 0; q < SORT_KPT / 4; ++q) {
-        uint32_t w = 0;
-#pragma unroll
-        for (uint32_t r = 0; r < 4; ++r) {
-            const uint32_t k = q * 4 + r;
-            const bool valid = full || (warp_base + k * 32u) < n;
-            w |= hist_slot(valid ? digit_in(key[k]) : mask) << (8u * r);
+            for (uint32_t c = 0; c < SORT_CHAINS; ++c) {
+                const bool has = seg_tiles[c + 1] - seg_tiles[c] > t.k;
+                if (!found && has) {
+                    if (idx == 0) { t.chain = c; found = true; }
+                    else --idx;
+                }
+            }
         }
-        dpack[q] = w;
-    }
-    auto digit_at = [&](uint32_t k) { return (dpack[k >> 2] >> (8u * (k & 3u))) & 0xffu; };
-
-    // ---- early counts: per-warp digit histograms ----------------------------------------------------
 #pragma unroll
-    for (uint32_t k = 0; k < SORT_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_at(k)], 1u);
-
-    // values (pair input): issue the loads now, their latency hides behind the per-bin phases
-    uint32_t val[IN_PAIRS ? SORT_KPT : 1];
-    if (IN_PAIRS) {
-        if (full) {
+        for (uint32_t c = 0; c < SORT_CHAINS; ++c)
+            if (c == t.chain) { t.begin = seg_start[c]; t.end = seg_start[c + 1]; t.row0 = seg_tiles[c]; }
+        return t;
+    };
+    // key loads of a tile, warp-striped: item k of lane l is element warp * 32 * KPT + 32 k + l of the tile; elements at or
+    // beyond the segment's end are padding that sorts last
+    uint64_t key[SORT_KPT];
+    auto load_keys = [&](const TileId& t) {
+        const uint32_t base = t.begin + t.k * SORT_TILE + warp * (32u * SORT_KPT) + lane;
+        if (t.end - (t.begin + t.k * SORT_TILE) >= SORT_TILE) {
 #pragma unroll
-            for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = src_vals[warp_base + k * 32u];
+            for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = src_keys[base + k * 32u];
         } else {
 #pragma unroll
-            for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = (warp_base + k * 32u) < n ? src_vals[warp_base + k * 32u] : 0u;
+            for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = (base + k * 32u) < t.end ? src_keys[base + k * 32u] : ~0ull;
         }
-    }
-    __syncthreads();
+    };
 
-    // ---- per-bin (thread == bin): exclusive prefix over warps, publish the tile aggregate, scan the bins -------------
-    uint32_t* lb = lookback_pass + (size_t)part * SORT_BINS;
-    uint32_t bin_count = 0;
-    const uint32_t my_slot = hist_slot(tid);
-#pragma unroll
-    for (uint32_t w = 0; w < SORT_WARPS; ++w) {
-        const uint32_t c = sm.warp_hist[w][my_slot];
-        sm.warp_hist[w][my_slot] = bin_count;
-        bin_count += c;
-    }
-    const uint32_t bin_count_valid = (tid == mask) ? bin_count - (SORT_TILE - n_valid) : bin_count;  // padding lives in the top bin
-    if (tid == 0) { WS_STAMP(part, 1); WS_STAMP(part, 2); }
-    st_relaxed_u32(lb + tid, ((part == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) << 30) | bin_count_valid);
-    uint32_t incl = bin_count;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (uint32_t)d) incl += up;
-    }
-    if (lane == 31) sm.scan[warp] = incl;
-    uint32_t bin_base = incl - bin_count;
     __syncthreads();
-#pragma unroll
-    for (uint32_t w = 0; w < SORT_BINS / 32; ++w)
-        if (w < warp) bin_base += sm.scan[w];
-#pragma unroll
-    for (uint32_t w = 0; w < SORT_WARPS; ++w) sm.warp_hist[w][my_slot] += bin_base;
-#if TPDCU_SORT_LOOKBACK_VEC
-    sm.bin_count[tid] = bin_count_valid;
-    sm.bin_base[tid] = bin_base;
-#endif
-    __syncthreads();
-
-    // ---- stable ranking: peers with the same digit inside a 32-key row, rows in order; elements go straight to smem ---
-#if TPDCU_SORT_LOOKBACK_EARLY
-    // The first round trip of the look-back is issued now and consumed after the ranking: the predecessors published their
-    // aggregates about when this tile did, and the ranking below does not depend on them.
-    uint32_t v_early[LOOKBACK_BATCH];
-#pragma unroll
-    for (int j = 0; j < (int)LOOKBACK_BATCH; ++j)
-        v_early[j] = part > 0 ? ld_relaxed_u32(lookback_pass + (size_t)max((int)part - 1 - j, 0) * SORT_BINS + tid) : 0u;
-#endif
-    uint32_t rank[OUT_PAIRS ? SORT_KPT : 1];
-#if TPDCU_SORT_RANK_ATOMS
-    // One shared-memory atomic per key: ATOMS.POPC.INC with a destination register hands every lane the counter's value
-    // plus the number of LOWER lanes of the same instruction that hit the same counter, i.e. the stable rank, and a warp's
-    // atomics execute in program order, so rows stay ordered too (profiles/micro/atoms_rank.cu: 7-20 cycles per row and SM
-    // against 30-42 for eight ballots + bit logic; lane order held on all 1.2e8 rows checked, and tpdcu_create re-checks it
-    // on the device it runs on). Batches: the atomics of a batch are in flight together, then their keys are scattered.
-    {
-        const uint32_t hist_base = (uint32_t)__cvta_generic_to_shared(&sm.warp_hist[warp][0]);
-#pragma unroll
-        for (uint32_t k0 = 0; k0 < SORT_KPT; k0 += SORT_RANK_BATCH) {
-            uint32_t r[SORT_RANK_BATCH];
-#pragma unroll
-            for (uint32_t j = 0; j < SORT_RANK_BATCH; ++j)
-                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r[j]) : "r"(hist_base + 4u * digit_at(k0 + j)) : "memory");
-#pragma unroll
-            for (uint32_t j = 0; j < SORT_RANK_BATCH; ++j) {
-                if (OUT_PAIRS) rank[k0 + j] = r[j];
-                sm.keys[r[j]] = key[k0 + j];
-            }
-        }
-    }
-#else
-#pragma unroll
-    for (uint32_t k = 0; k < SORT_KPT; ++k) {
-        const uint32_t d = digit_at(k);
-        // peers = lanes of this row holding the same digit: eight ballots + bit logic on the ALU pipe (match.any executes on
-        // the address-divergence unit: ADU 39 %, LSU 57 % — the ballot form was 20 % faster). Kept as the variant for a device
-        // whose shared-memory atomics do not return lane-ordered values.
-        uint32_t peers = 0xffffffffu;
-#pragma unroll
-        for (uint32_t bit = 0; bit < SORT_RADIX_BITS; ++bit)
-            asm("{\n\t.reg .pred p;\n\t.reg .b32 b;\n\t"
-                "and.b32 b, %1, %2;\n\tsetp.ne.u32 p, b, 0;\n\t"
-                "vote.sync.ballot.b32 b, p, 0xffffffff;\n\t"
-                "@!p not.b32 b, b;\n\tand.b32 %0, %0, b;\n\t}"
-                : "+r"(peers) : "r"(d), "r"(1u << bit));
-        const uint32_t lower = __popc(peers & lanemask_lt());
-        const uint32_t base = sm.warp_hist[warp][d];
+    uint32_t part = sm.part;
+    if (part >= total_tiles) return;
+    TileId cur = locate(part);
+    load_keys(cur);
+    {   // this warp's counters start at zero (a warp only ever counts into its own row)
+        uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[warp][0]);
+        z[lane] = make_uint4(0, 0, 0, 0);
+        z[lane + 32] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        if (lower == 0) sm.warp_hist[warp][d] = base + __popc(peers);
-        __syncwarp();
-        const uint32_t r = base + lower;
-        if (OUT_PAIRS) rank[k] = r;
-        sm.keys[r] = key[k];
-    }
-#endif
-
-#if TPDCU_SORT_LOOKBACK_VEC
-    // ---- decoupled look-back, four bins per thread: 64 threads, one 16-byte descriptor load per row and thread -------------
-    // The walk costs what its loads cost (strong loads served by L2, ~0.9 us per batch of eight rows under load, a third of a
-    // tile's life): a quarter of the requests for the same rows. Words are summed with their flags; the flags' share
-    // (rows x flag << 30, modulo 2^32 like the sums) is taken out at the end. A row is consumed once its four words carry the
-    // same valid flag (a tile publishes its descriptors together), else it is fetched again.
-    if (tid == 0) { WS_STAMP(part, 3); WS_STAMP(part, 5); }
-    if (tid < SORT_BINS / 4) {
-        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, trace_rows = 0;
-        (void)trace_rows;
-        if (part > 0) {
-            int look = (int)part - 1;
-            uint32_t agg_rows = 0;
-            bool done = false;
-            while (!done) {
-                uint4 v[LOOKBACK_BATCH];
-#pragma unroll
-                for (int j = 0; j < (int)LOOKBACK_BATCH; ++j) v[j] = ld_relaxed_v4(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid * 4u);
-#pragma unroll
-                for (int j = 0; j < (int)LOOKBACK_BATCH; ++j) {
-                    if (!done) {
-                        uint4 x = v[j];
-                        uint32_t all_and;
-                        for (;;) {
-                            all_and = x.x & x.y & x.z & x.w;
-                            const uint32_t all_or = x.x | x.y | x.z | x.w;
-                            if (((all_and ^ all_or) >> 30) == 0u && (all_and >> 30) != FLAG_INVALID) break;
-                            x = ld_relaxed_v4(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid * 4u);
-                        }
-                        e0 += x.x; e1 += x.y; e2 += x.z; e3 += x.w;
-                        if ((all_and >> 30) == FLAG_PREFIX) done = true;  // tile 0 always carries a PREFIX
-                        else ++agg_rows;
-                        ++trace_rows;
-                    }
-                }
-                look -= (int)LOOKBACK_BATCH;
-            }
-            const uint32_t flags = (agg_rows * FLAG_AGGREGATE + FLAG_PREFIX) << 30;
-            e0 -= flags; e1 -= flags; e2 -= flags; e3 -= flags;
-            const uint4 c = *reinterpret_cast<const uint4*>(&sm.bin_count[tid * 4u]);
-            st_relaxed_v4(lb + tid * 4u, make_uint4((FLAG_PREFIX << 30) | (e0 + c.x), (FLAG_PREFIX << 30) | (e1 + c.y),
-                                                    (FLAG_PREFIX << 30) | (e2 + c.z), (FLAG_PREFIX << 30) | (e3 + c.w)));
-        }
-        const uint4 bb = *reinterpret_cast<const uint4*>(&sm.bin_base[tid * 4u]);
-        const uint4 h = *reinterpret_cast<const uint4*>(&ctl->hist[pass][tid * 4u]);
-        *reinterpret_cast<uint4*>(&sm.global_base[tid * 4u]) = make_uint4(h.x + e0 - bb.x, h.y + e1 - bb.y, h.z + e2 - bb.z, h.w + e3 - bb.w);
-        if (tid == 0) { WS_STAMP(part, 4); WS_STAMP(part, 6); WS_NOTE(part, 8, (unsigned long long)trace_rows); WS_NOTE(part, 9, 0ull); WS_NOTE(part, 10, (unsigned long long)blockIdx.x); }
-    }
-#else
-    // ---- decoupled look-back, one thread per bin -----------------------------------------------------
-    {
-        if (tid == 0) { WS_STAMP(part, 3); WS_STAMP(part, 5); }
-        uint32_t excl = 0, trace_rows = 0;
-        (void)trace_rows;
-        if (part > 0) {
-            // Tiles in flight publish their aggregate well before their prefix, so the walk back to the nearest PREFIX is
-            // several tiles deep: read LOOKBACK_BATCH descriptors per round trip, consume them in order.
-            int look = (int)part - 1;
-            bool done = false;
-#if TPDCU_SORT_LOOKBACK_EARLY
-            bool first = true;
-#endif
-            while (!done) {
-                uint32_t v[LOOKBACK_BATCH];
-#if TPDCU_SORT_LOOKBACK_EARLY
-                if (first) {
-#pragma unroll
-                    for (int j = 0; j < (int)LOOKBACK_BATCH; ++j) v[j] = v_early[j];
-                    first = false;
-                } else
-#endif
-                {
-#pragma unroll
-                    for (int j = 0; j < (int)LOOKBACK_BATCH; ++j)
-                        v[j] = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
-                }
-#pragma unroll
-                for (int j = 0; j < (int)LOOKBACK_BATCH; ++j) {
-                    if (!done) {
-                        uint32_t x = v[j];
-                        while ((x >> 30) == FLAG_INVALID) x = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
-                        excl += x & LOOKBACK_VALUE_MASK;
-                        done = (x >> 30) == FLAG_PREFIX;  // tile 0 always carries a PREFIX, so look - j never goes below 0 unconsumed
-                        ++trace_rows;
-                    }
-                }
-                look -= (int)LOOKBACK_BATCH;
-            }
-            st_relaxed_u32(lb + tid, (FLAG_PREFIX << 30) | (excl + bin_count_valid));
-        }
-        sm.global_base[tid] = ctl->hist[pass][tid] + excl - bin_base;
-        if (tid == 0) { WS_STAMP(part, 4); WS_STAMP(part, 6); WS_NOTE(part, 8, (unsigned long long)trace_rows); WS_NOTE(part, 9, 0ull); WS_NOTE(part, 10, (unsigned long long)blockIdx.x); }
-    }
-#endif
-    __syncthreads();
-
-    // ---- write-out: position i of the locally sorted tile goes to global_base[digit] + i (contiguous per bin) ---------
-    uint32_t pos[OUT_PAIRS ? SORT_KPT : 1];
-    if (full) {  // every tile but the last: no per-key bounds branch
-#pragma unroll
-        for (uint32_t k = 0; k < SORT_KPT; ++k) {
-            const uint32_t i = tid + k * SORT_THREADS;
-            const uint64_t kk = sm.keys[i];
-            const uint32_t p = sm.global_base[digit_out(kk)] + i;
-            if (OUT_PAIRS) pos[k] = p;
-            dst_keys[p] = kk;
-        }
-    } else {
-#pragma unroll
-        for (uint32_t k = 0; k < SORT_KPT; ++k) {
-            const uint32_t i = tid + k * SORT_THREADS;
-            if (i < n_valid) {
-                const uint64_t kk = sm.keys[i];
-                const uint32_t p = sm.global_base[digit_out(kk)] + i;
-                if (OUT_PAIRS) pos[k] = p;
-                dst_keys[p] = kk;
-            }
-        }
-    }
-    if (tid == 0) WS_STAMP(part, 7);
-    if (OUT_PAIRS) {
-#pragma unroll
-        for (uint32_t k = 0; k < SORT_KPT; ++k) sm.vals[rank[k]] = val[k];
-        __syncthreads();
-#pragma unroll
-        for (uint32_t k = 0; k < SORT_KPT; ++k) {
-            const uint32_t i = tid + k * SORT_THREADS;
-            if (i < n_valid) dst_vals[pos[k]] = sm.vals[i];
-        }
-    }
-}
-
-#if TPDCU_SORT_WS
-// ---------------------------------------------------------------------------------------------------
-// one onesweep pass over single words, warp-specialised and persistent (the frame's two sorts)
-// ---------------------------------------------------------------------------------------------------
-//
-// The per-tile kernel above spends two thirds of its warp time waiting: for its ticket, for its keys (a third of all stall
-// samples) and in the look-back (a fifth), with two CTAs per SM to cover for each other (ncu, profiles/r2_onesweep_*.txt).
-// Here ONE CTA per SM stays resident and runs two independent consumer groups of eight warps, each with a helper warp:
-//   helper   draws the group's next ticket and streams that tile into the group's spare key buffer with TMA bulk copies
-//            (cp.async.bulk -> mbarrier) while the group still works on the current tile; then resolves the current tile's
-//            decoupled look-back — eight bins per lane, 128-bit descriptor loads — while the group ranks its keys.
-//   group    keys shared -> registers, counting atomics, per-bin prefix + aggregate publication, ranking atomics + scatter
-//            into the buffer the keys came from, (wait for the helper's bases), coalesced write-out.
-// Tickets are drawn when a buffer frees up, not in lock-step, so tiles stay staggered across the SMs and the look-back
-// stays shallow (persistent CTAs with a static tile assignment walked 67 descriptors deep).
-constexpr uint32_t WS_GROUPS = 2;
-constexpr uint32_t WS_GROUP_THREADS = SORT_THREADS;                 // one thread per bin in the per-bin phases
-constexpr uint32_t WS_GROUP_WARPS = WS_GROUP_THREADS / 32;
-constexpr uint32_t WS_THREADS = WS_GROUPS * (WS_GROUP_THREADS + 32);  // consumer warps first, then one helper warp per group
-constexpr uint32_t WS_KPT = SORT_KPT_WORDS;
-constexpr uint32_t WS_TILE = SORT_TILE_WORDS;
-constexpr uint32_t WS_END = 0xffffffffu;
-#ifndef TPDCU_WS_LOOKBACK_BATCH
-#define TPDCU_WS_LOOKBACK_BATCH 8
-#endif
-constexpr int WS_LB_BATCH = TPDCU_WS_LOOKBACK_BATCH;
-#ifndef TPDCU_WS_HELPER_LOOKBACK
-#define TPDCU_WS_HELPER_LOOKBACK 0       // 1: the helper warp resolves the look-back (eight bins per lane); 0: the group does, one thread per bin
-#endif
-#ifndef TPDCU_WS_LOOKBACK_EARLY
-#define TPDCU_WS_LOOKBACK_EARLY 1        // group look-back: first batch of descriptor loads issued before the ranking
-#endif
-#ifndef TPDCU_WS_PREFETCH_TILES
-#define TPDCU_WS_PREFETCH_TILES 296
-#endif
-constexpr uint32_t WS_PREFETCH_TILES = TPDCU_WS_PREFETCH_TILES;      // 148 SMs x 2 groups
-constexpr uint32_t WS_TMA_CHUNKS = 8;                                // bulk copies per tile (one per helper lane)
-static_assert((WS_TILE * sizeof(uint64_t)) % (WS_TMA_CHUNKS * 16) == 0, "TMA chunks are multiples of 16 bytes");
-
-struct WsGroupSmem {
-    alignas(128) uint64_t keys[2][WS_TILE];                          // raw tile -> locally sorted tile, double-buffered
-    alignas(16) uint32_t warp_hist[WS_GROUP_WARPS][SORT_BINS];
-    alignas(16) uint32_t global_base[SORT_BINS];                     // helper -> group: where bin b's run of this tile starts, minus its tile-local offset
-    alignas(16) uint32_t bin_count[SORT_BINS];                       // group -> helper: valid keys of this tile per bin
-    alignas(16) uint32_t bin_base[SORT_BINS];                        // group -> helper: tile-local offset of the bin's run
-    uint32_t scan[SORT_BINS / 32];
-    uint32_t part[2];                                                // ticket of the tile in keys[i & 1], WS_END when there is none
-    alignas(8) uint64_t raw_full[2], raw_empty[2], agg_ready, lb_done;
-};
-struct WsSmem { WsGroupSmem g[WS_GROUPS]; };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ready = 0;
-    while (!ready)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ready) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void group_sync(uint32_t group) {  // named barrier of one consumer group (barrier 0 is __syncthreads)
-    asm volatile("bar.sync %0, %1;" ::"r"(group + 1u), "r"(WS_GROUP_THREADS) : "memory");
-}
-// every lane of the warp holds the same flag value
-__device__ __forceinline__ bool __match_all_flags(uint32_t flag) {
-    return __all_sync(0xffffffffu, flag == __shfl_sync(0xffffffffu, flag, 0));
-}
-
-__global__ void __launch_bounds__(WS_THREADS, 1)
-onesweep_ws_kernel(uint64_t* keys0, uint64_t* keys1, SortCtl* ctl, const SortPlan* __restrict__ plan, uint32_t* lookback_pass, uint32_t pass) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    WsSmem& smem = *reinterpret_cast<WsSmem*>(smem_raw);
-    if (plan->skip[pass]) return;
-    const uint32_t n = plan->n;
-    const uint32_t src = plan->src_sel[pass];
-    const uint64_t* __restrict__ src_keys = src ? keys1 : keys0;
-    uint64_t* __restrict__ dst_keys = src ? keys0 : keys1;
-    const uint32_t bias = plan->bias, total_bits = plan->total_bits;
-    const uint32_t shift = pass * SORT_RADIX_BITS, mask = pass_mask(pass, total_bits);
-    auto digit_of = [&](uint64_t k) { return (uint32_t)(sort_key<true>(k, bias) >> shift) & mask; };
-
-    const uint32_t warp_id = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const bool helper = warp_id >= WS_GROUPS * WS_GROUP_WARPS;
-    const uint32_t group = helper ? warp_id - WS_GROUPS * WS_GROUP_WARPS : warp_id / WS_GROUP_WARPS;
-    WsGroupSmem& sm = smem.g[group];
-    if (threadIdx.x == 0) {
-        for (uint32_t g = 0; g < WS_GROUPS; ++g) {
-            WsGroupSmem& x = smem.g[g];
-            mbar_init(&x.raw_full[0], 1); mbar_init(&x.raw_full[1], 1);
-            mbar_init(&x.raw_empty[0], WS_GROUP_WARPS); mbar_init(&x.raw_empty[1], WS_GROUP_WARPS);
-            mbar_init(&x.agg_ready, WS_GROUP_WARPS); mbar_init(&x.lb_done, TPDCU_WS_HELPER_LOOKBACK ? 1 : WS_GROUP_WARPS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (helper) {
-        // ---------------- helper warp: ticket + TMA of the next tile, look-back of the tile in flight ----------------
-        // The next ticket is drawn when the look-back of the current tile has completed. Look-backs complete in (roughly)
-        // ticket order, so tickets are handed out in the order the groups will really start their tiles and nobody spins
-        // on the aggregate of a tile whose group is still busy with another one (tickets drawn a whole tile ahead were
-        // uncorrelated with that order: every generation of tiles waited for its slowest member, 240 us per pass).
-        auto draw = [&]() {
-            uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(&ctl->ticket[pass], 1u);
-            return __shfl_sync(0xffffffffu, t, 0);
-        };
-        uint32_t part = draw();
-        for (uint32_t it = 0;; ++it) {
-            const uint32_t b = it & 1u;
-            // keys[b] last held tile it - 2: the group releases the buffer when it has written that tile out
-            if (it >= 2) mbar_wait(&sm.raw_empty[b], ((it - 2) >> 1) & 1u);
-            const bool more = (uint64_t)part * WS_TILE < n;
-            if (lane == 0 && more) { WS_STAMP(part, 0); WS_NOTE(part, 10, (unsigned long long)(blockIdx.x * WS_GROUPS + group)); }
-            if (lane == 0) {
-                sm.part[b] = more ? part : WS_END;
-                if (more) mbar_expect_tx(&sm.raw_full[b], (uint32_t)(WS_TILE * sizeof(uint64_t)));
-                else mbar_arrive(&sm.raw_full[b]);
-            }
-            __syncwarp();
-            if (!more) break;
-            if (lane < WS_TMA_CHUNKS) {
-                // the key buffers are allocated in whole tiles: the last tile is copied whole, its tail is masked by the group
-                constexpr uint32_t chunk = (uint32_t)(WS_TILE * sizeof(uint64_t)) / WS_TMA_CHUNKS;
-                const unsigned char* g = reinterpret_cast<const unsigned char*>(src_keys + (size_t)part * WS_TILE) + lane * chunk;
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(reinterpret_cast<unsigned char*>(sm.keys[b]) + lane * chunk)), "l"(g), "r"(chunk), "r"(smem_u32(&sm.raw_full[b])) : "memory");
-            } else if (lane == WS_TMA_CHUNKS) {
-                // whoever draws the ticket one round of groups ahead finds its tile in L2
-                const uint64_t ahead = (uint64_t)(part + WS_PREFETCH_TILES) * WS_TILE;
-                if (ahead + WS_TILE <= n)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_keys + ahead), "r"((uint32_t)(WS_TILE * sizeof(uint64_t))) : "memory");
-            }
-#if TPDCU_WS_HELPER_LOOKBACK
-            // look-back of this tile while the group ranks it
-            mbar_wait(&sm.agg_ready, it & 1u);
-            if (lane == 0) WS_STAMP(part, 3);
-            // This lane owns bins 4 lane .. 4 lane + 3 and 128 + 4 lane .. 128 + 4 lane + 3: two 16-byte loads per descriptor row,
-            // each a contiguous 512 bytes across the warp.
-            uint32_t excl[8], trace_rows = 0, trace_retries = 0;
-            (void)trace_rows; (void)trace_retries;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) excl[q] = 0;
-            if (part > 0) {
-                // One warp walks all 256 bins, so the walk is kept warp-uniform and cheap: a tile's descriptors carry the same
-                // flag in every bin (they are published together), a row is only consumed once it is uniform (re-fetched while
-                // it has missing or mixed entries), the raw words are summed with their flags and the flags' contribution
-                // (rows x flag << 30, modulo 2^32 like the sums) is taken out at the end.
-                int look = (int)part - 1;
-                uint32_t agg_rows = 0, batch_no = 0;
-                (void)batch_no;
-                bool done = false;
-                while (!done) {
-                    if (lane == 0) WS_LB_STAMP(part, 2 * batch_no);
-                    uint4 v[WS_LB_BATCH][2];
-#pragma unroll
-                    for (int j = 0; j < WS_LB_BATCH; ++j) {
-                        const uint32_t* d = lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + lane * 4u;
-                        v[j][0] = ld_relaxed_v4(d);
-                        v[j][1] = ld_relaxed_v4(d + 128);
-                    }
-#pragma unroll
-                    for (int j = 0; j < WS_LB_BATCH; ++j) {
-                        if (!done) {
-                            const uint32_t* d = lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + lane * 4u;
-                            uint32_t all_and, all_or;
-                            for (;;) {
-                                all_and = v[j][0].x & v[j][0].y & v[j][0].z & v[j][0].w & v[j][1].x & v[j][1].y & v[j][1].z & v[j][1].w;
-                                all_or = v[j][0].x | v[j][0].y | v[j][0].z | v[j][0].w | v[j][1].x | v[j][1].y | v[j][1].z | v[j][1].w;
-                                // uniform row: the two flag bits agree in every word of every lane, and are not INVALID
-                                const bool uniform = ((all_and ^ all_or) >> 30) == 0u && (all_and >> 30) != FLAG_INVALID;
-                                if (__all_sync(0xffffffffu, uniform) && __match_all_flags(all_and >> 30)) break;
-                                v[j][0] = ld_relaxed_v4(d);
-                                v[j][1] = ld_relaxed_v4(d + 128);
-                                ++trace_retries;
-                            }
-                            ++trace_rows;
-                            excl[0] += v[j][0].x; excl[1] += v[j][0].y; excl[2] += v[j][0].z; excl[3] += v[j][0].w;
-                            excl[4] += v[j][1].x; excl[5] += v[j][1].y; excl[6] += v[j][1].z; excl[7] += v[j][1].w;
-                            if ((all_and >> 30) == FLAG_PREFIX) done = true;   // tile 0 always carries a PREFIX
-                            else ++agg_rows;
-                        }
-                    }
-                    look -= WS_LB_BATCH;
-                    if (lane == 0) WS_LB_STAMP(part, 2 * batch_no + 1);
-                    ++batch_no;
-                }
-                const uint32_t flags = (agg_rows * FLAG_AGGREGATE + FLAG_PREFIX) << 30;   // modulo 2^32, like the sums
-#pragma unroll
-                for (int q = 0; q < 8; ++q) excl[q] -= flags;
-                uint32_t* lb = lookback_pass + (size_t)part * SORT_BINS + lane * 4u;
-                const uint4 c0 = *reinterpret_cast<const uint4*>(&sm.bin_count[lane * 4u]), c1 = *reinterpret_cast<const uint4*>(&sm.bin_count[128u + lane * 4u]);
-                st_relaxed_v4(lb, make_uint4((FLAG_PREFIX << 30) | (excl[0] + c0.x), (FLAG_PREFIX << 30) | (excl[1] + c0.y),
-                                             (FLAG_PREFIX << 30) | (excl[2] + c0.z), (FLAG_PREFIX << 30) | (excl[3] + c0.w)));
-                st_relaxed_v4(lb + 128, make_uint4((FLAG_PREFIX << 30) | (excl[4] + c1.x), (FLAG_PREFIX << 30) | (excl[5] + c1.y),
-                                                   (FLAG_PREFIX << 30) | (excl[6] + c1.z), (FLAG_PREFIX << 30) | (excl[7] + c1.w)));
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint32_t bin = (q < 4 ? 0u : 128u) + lane * 4u + (uint32_t)(q & 3);
-                sm.global_base[bin] = ctl->hist[pass][bin] + excl[q] - sm.bin_base[bin];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.lb_done);
-            if (lane == 0) { WS_STAMP(part, 4); WS_NOTE(part, 8, (unsigned long long)trace_rows); WS_NOTE(part, 9, (unsigned long long)trace_retries); }
-#else
-            mbar_wait(&sm.lb_done, it & 1u);   // the group has resolved this tile's look-back: tickets follow that order
-#endif
-            part = draw();
-        }
-        return;
     }
 
-    // ---------------- consumer group ----------------
-    const uint32_t tid = threadIdx.x - group * WS_GROUP_THREADS, warp = tid >> 5;
-    const uint32_t my_slot = hist_slot(tid);
-    const uint32_t hist_row = smem_u32(&sm.warp_hist[warp][0]);
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t b = it & 1u;
-        mbar_wait(&sm.raw_full[b], (it >> 1) & 1u);
-        const uint32_t part = sm.part[b];
-        if (part == WS_END) break;
-        if (tid == 0) WS_STAMP(part, 1);
-        const uint32_t tile_base = part * WS_TILE;
-        const uint32_t n_valid = min(WS_TILE, n - tile_base);
-        const bool full = n_valid == WS_TILE;
-        uint64_t* tile = sm.keys[b];
+    for (;;) {
+        const uint32_t tile_base = cur.begin + cur.k * SORT_TILE;
+        const uint32_t n = cur.end;                       // elements at or beyond the segment's end are padding
+        const uint32_t n_valid = min(SORT_TILE, cur.end - tile_base);
+        const uint32_t row = cur.row0 + cur.k;            // this tile's descriptor row; its chain's rows are row0 .. row
+        const uint32_t chain = cur.chain, k_tile = cur.k, row0 = cur.row0;
+        const uint32_t warp_base = tile_base + warp * (32u * SORT_KPT) + lane;
+        const bool full = n_valid == SORT_TILE;
+        if (tid == 0) WS_STAMP(part, 0);
 
-        // ---- keys: shared -> registers (warp-striped: item k of lane l is element warp * 32 * KPT + 32 k + l of the tile) ----
-        uint64_t key[WS_KPT];
-        const uint32_t local = warp * (32u * WS_KPT) + lane;
+        // ---- digits, computed once and packed four to a register; padding (only in a segment's last tile) goes to the top bin
+        // What is packed is the digit's COUNTER SLOT, hist_slot(d) = d ^ ((d >> 5) & 3): the per-warp counters are only ever
+        // indexed by it. The tile sort's low digit is (tile & 63) << 2 | top depth bits, and neighbours in depth order share
+        // those depth bits, so the digits of a row sit at stride 4: unswizzled they fall on 8 of the 32 banks (ncu: 7.7
+        // wavefronts per ranking atomic, 5.6 per counting atomic). XOR-ing bits 5-6 into bits 0-1 spreads a stride-4 run over
+        // all banks and still maps 32 consecutive bins (a warp of the thread == bin phases) onto 32 distinct banks.
+        uint32_t dpack[SORT_KPT / 4];
 #pragma unroll
-        for (uint32_t k = 0; k < WS_KPT; ++k) key[k] = tile[local + k * 32u];
-        if (!full) {
-#pragma unroll
-            for (uint32_t k = 0; k < WS_KPT; ++k)
-                if (local + k * 32u >= n_valid) key[k] = ~0ull;
-        }
-        {   // this warp's counters start at zero
-            uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[warp][0]);
-            z[lane] = make_uint4(0, 0, 0, 0);
-            z[lane + 32] = make_uint4(0, 0, 0, 0);
-        }
-        __syncwarp();
-        // ---- counter slots of the digits, four to a register; padding (last tile only) goes to the top bin ----
-        uint32_t dpack[WS_KPT / 4];
-#pragma unroll
-        for (uint32_t q = 0; q < WS_KPT / 4; ++q) {
+        for (uint32_t q = 0; q < SORT_KPT / 4; ++q) {
             uint32_t w = 0;
 #pragma unroll
             for (uint32_t r = 0; r < 4; ++r) {
                 const uint32_t k = q * 4 + r;
-                const bool valid = full || (local + k * 32u) < n_valid;
-                w |= hist_slot(valid ? digit_of(key[k]) : mask) << (8u * r);
+                const bool valid = full || (warp_base + k * 32u) < n;
+                w |= hist_slot(valid ? digit_in(key[k]) : mask) << (8u * r);
             }
             dpack[q] = w;
         }
-        auto slot_at = [&](uint32_t k) { return (dpack[k >> 2] >> (8u * (k & 3u))) & 0xffu; };
-#pragma unroll
-        for (uint32_t k = 0; k < WS_KPT; ++k) atomicAdd(&sm.warp_hist[warp][slot_at(k)], 1u);
-        group_sync(group);   // every key of the tile is in registers and counted
+        auto digit_at = [&](uint32_t k) { return (dpack[k >> 2] >> (8u * (k & 3u))) & 0xffu; };
 
-        // ---- per bin (thread == bin): prefix over the warps, publish the tile aggregate, scan the bins ----
+        // ---- early counts: per-warp digit histograms ----------------------------------------------------
+#pragma unroll
+        for (uint32_t k = 0; k < SORT_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_at(k)], 1u);
+
+        // values (pair input): issue the loads now, their latency hides behind the per-bin phases
+        uint32_t val[IN_PAIRS ? SORT_KPT : 1];
+        if (IN_PAIRS) {
+            if (full) {
+#pragma unroll
+                for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = src_vals[warp_base + k * 32u];
+            } else {
+#pragma unroll
+                for (uint32_t k = 0; k < SORT_KPT; ++k) val[k] = (warp_base + k * 32u) < n ? src_vals[warp_base + k * 32u] : 0u;
+            }
+        }
+        __syncthreads();
+
+        // ---- per-bin (thread == bin): exclusive prefix over warps, publish the tile aggregate, scan the bins -------------
+        uint32_t* lb = lookback_pass + (size_t)row * SORT_BINS;
         uint32_t bin_count = 0;
 #pragma unroll
-        for (uint32_t w = 0; w < WS_GROUP_WARPS; ++w) {
+        for (uint32_t w = 0; w < SORT_WARPS; ++w) {
             const uint32_t c = sm.warp_hist[w][my_slot];
             sm.warp_hist[w][my_slot] = bin_count;
             bin_count += c;
         }
-        const uint32_t bin_count_valid = (tid == mask) ? bin_count - (WS_TILE - n_valid) : bin_count;
-        st_relaxed_u32(lookback_pass + (size_t)part * SORT_BINS + tid, ((part == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) << 30) | bin_count_valid);
+        const uint32_t bin_count_valid = (tid == mask) ? bin_count - (SORT_TILE - n_valid) : bin_count;  // padding lives in the top bin
+        if (tid == 0) { WS_STAMP(part, 1); WS_STAMP(part, 2); }
+        st_relaxed_u32(lb + tid, ((k_tile == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) << 30) | bin_count_valid);
         uint32_t incl = bin_count;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -879,117 +493,133 @@ onesweep_ws_kernel(uint64_t* keys0, uint64_t* keys1, SortCtl* ctl, const SortPla
         }
         if (lane == 31) sm.scan[warp] = incl;
         uint32_t bin_base = incl - bin_count;
-        group_sync(group);
+        __syncthreads();
 #pragma unroll
         for (uint32_t w = 0; w < SORT_BINS / 32; ++w)
             if (w < warp) bin_base += sm.scan[w];
-        sm.bin_count[tid] = bin_count_valid;
-        sm.bin_base[tid] = bin_base;
 #pragma unroll
-        for (uint32_t w = 0; w < WS_GROUP_WARPS; ++w) sm.warp_hist[w][my_slot] += bin_base;
-        __syncwarp();
-#if TPDCU_WS_HELPER_LOOKBACK
-        if (lane == 0) mbar_arrive(&sm.agg_ready);   // the helper may resolve this tile's look-back now
+        for (uint32_t w = 0; w < SORT_WARPS; ++w) sm.warp_hist[w][my_slot] += bin_base;
+        uint32_t next_ticket = 0;
+#if TPDCU_SORT_DRAW_EARLY
+        if (tid == 0) next_ticket = atomicAdd(&ctl->ticket[pass], 1u);   // the next ticket travels while this tile is ranked
 #endif
-        if (tid == 0) WS_STAMP(part, 2);
-        group_sync(group);
-#if !TPDCU_WS_HELPER_LOOKBACK && TPDCU_WS_LOOKBACK_EARLY
-        // first round trip of the look-back: issued now, consumed after the ranking
-        uint32_t v_early[WS_LB_BATCH];
-#pragma unroll
-        for (int j = 0; j < WS_LB_BATCH; ++j)
-            v_early[j] = part > 0 ? ld_relaxed_u32(lookback_pass + (size_t)max((int)part - 1 - j, 0) * SORT_BINS + tid) : 0u;
-#endif
+        __syncthreads();
 
-        // ---- stable ranking (one returning shared-memory atomic per key) + scatter into the buffer the keys came from ----
+        // ---- stable ranking: one returning shared-memory atomic per key; elements go straight to smem ---------------------
+        // ATOMS.POPC.INC with a destination register hands every lane the counter's value plus the number of LOWER lanes of
+        // the same instruction that hit the same counter, i.e. the stable rank, and a warp's atomics execute in program order,
+        // so rows stay ordered too (profiles/micro/atoms_rank.cu: 7-20 cycles per row and SM against 30-42 for eight ballots +
+        // bit logic; lane order held on all 1.2e8 rows checked). Batches: the atomics of a batch are in flight together, then
+        // their keys are scattered.
+        uint32_t rank[OUT_PAIRS ? SORT_KPT : 1];
 #pragma unroll
-        for (uint32_t k0 = 0; k0 < WS_KPT; k0 += SORT_RANK_BATCH) {
+        for (uint32_t k0 = 0; k0 < SORT_KPT; k0 += SORT_RANK_BATCH) {
             uint32_t r[SORT_RANK_BATCH];
 #pragma unroll
             for (uint32_t j = 0; j < SORT_RANK_BATCH; ++j)
-                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r[j]) : "r"(hist_row + 4u * slot_at(k0 + j)) : "memory");
+                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r[j]) : "r"(hist_row + 4u * digit_at(k0 + j)) : "memory");
 #pragma unroll
-            for (uint32_t j = 0; j < SORT_RANK_BATCH; ++j) tile[r[j]] = key[k0 + j];
-        }
-        if (tid == 0) WS_STAMP(part, 5);
-#if TPDCU_WS_HELPER_LOOKBACK
-        group_sync(group);
-        mbar_wait(&sm.lb_done, it & 1u);
-#else
-        {   // ---- decoupled look-back, one thread per bin ----
-            if (tid == 0) WS_STAMP(part, 3);
-            uint32_t excl = 0, trace_rows = 0;
-            (void)trace_rows;
-            if (part > 0) {
-                int look = (int)part - 1;
-                bool done = false;
-#if TPDCU_WS_LOOKBACK_EARLY
-                bool first = true;
-#endif
-                while (!done) {
-                    uint32_t v[WS_LB_BATCH];
-#if TPDCU_WS_LOOKBACK_EARLY
-                    if (first) {
-#pragma unroll
-                        for (int j = 0; j < WS_LB_BATCH; ++j) v[j] = v_early[j];
-                        first = false;
-                    } else
-#endif
-                    {
-#pragma unroll
-                        for (int j = 0; j < WS_LB_BATCH; ++j)
-                            v[j] = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
-                    }
-#pragma unroll
-                    for (int j = 0; j < WS_LB_BATCH; ++j) {
-                        if (!done) {
-                            uint32_t x = v[j];
-                            while ((x >> 30) == FLAG_INVALID) x = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, 0) * SORT_BINS + tid);
-                            excl += x & LOOKBACK_VALUE_MASK;
-                            done = (x >> 30) == FLAG_PREFIX;  // tile 0 always carries a PREFIX
-                            ++trace_rows;
-                        }
-                    }
-                    look -= WS_LB_BATCH;
-                }
-                st_relaxed_u32(lookback_pass + (size_t)part * SORT_BINS + tid, (FLAG_PREFIX << 30) | (excl + bin_count_valid));
+            for (uint32_t j = 0; j < SORT_RANK_BATCH; ++j) {
+                if (OUT_PAIRS) rank[k0 + j] = r[j];
+                sm.keys[r[j]] = key[k0 + j];
             }
-            sm.global_base[tid] = ctl->hist[pass][tid] + excl - bin_base;
-            if (tid == 0) { WS_STAMP(part, 4); WS_NOTE(part, 8, (unsigned long long)trace_rows); WS_NOTE(part, 9, 0ull); }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.lb_done);   // the helper draws the group's next ticket now
         }
-        group_sync(group);
+        {   // this warp's counters are free again: zero them for the next tile
+            __syncwarp();
+            uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[warp][0]);
+            z[lane] = make_uint4(0, 0, 0, 0);
+            z[lane + 32] = make_uint4(0, 0, 0, 0);
+        }
+#if !TPDCU_SORT_DRAW_EARLY
+        if (tid == 0) next_ticket = atomicAdd(&ctl->ticket[pass], 1u);   // travels while this tile's look-back runs
 #endif
-        if (tid == 0) WS_STAMP(part, 6);
+        if (tid == 0) { WS_STAMP(part, 3); WS_STAMP(part, 5); }
 
-        // ---- write-out: position i of the locally sorted tile goes to global_base[digit] + i ----
-        if (full) {
+        // ---- decoupled look-back, one thread per bin -----------------------------------------------------
+        uint32_t excl = 0, trace_rows = 0;
+        (void)trace_rows;
+        if (k_tile > 0) {
+            // Tiles in flight publish their aggregate well before their prefix, so the walk back to the nearest PREFIX is
+            // several tiles deep: read LOOKBACK_BATCH descriptors per round trip, consume them in order. The walk stays inside
+            // the tile's own chain: rows row0 .. row - 1, and row0 (the segment's first tile) always carries a PREFIX.
+            int look = (int)row - 1;
+            const int first_row = (int)row0;
+            bool done = false;
+            while (!done) {
+                uint32_t v[LOOKBACK_BATCH];
 #pragma unroll
-            for (uint32_t k = 0; k < WS_KPT; ++k) {
-                const uint32_t i = tid + k * WS_GROUP_THREADS;
-                const uint64_t kk = tile[i];
-                dst_keys[sm.global_base[digit_of(kk)] + i] = kk;
+                for (int j = 0; j < (int)LOOKBACK_BATCH; ++j)
+                    v[j] = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, first_row) * SORT_BINS + tid);
+#pragma unroll
+                for (int j = 0; j < (int)LOOKBACK_BATCH; ++j) {
+                    if (!done) {
+                        uint32_t x = v[j];
+                        while ((x >> 30) == FLAG_INVALID) x = ld_relaxed_u32(lookback_pass + (size_t)max(look - j, first_row) * SORT_BINS + tid);
+                        excl += x & LOOKBACK_VALUE_MASK;
+                        done = (x >> 30) == FLAG_PREFIX;  // reached at row0 at the latest, so look - j never goes below it unconsumed
+                        ++trace_rows;
+                    }
+                }
+                look -= (int)LOOKBACK_BATCH;
+            }
+            st_relaxed_u32(lb + tid, (FLAG_PREFIX << 30) | (excl + bin_count_valid));
+        }
+        // bin's output run + keys of the earlier segments in that bin + keys of this segment's earlier tiles - tile-local offset
+        sm.global_base[tid] = ctl->hist[pass][tid] + ctl->chain_hist[pass * chains + chain][tid] + excl - bin_base;
+        if (tid == 0) { WS_STAMP(part, 4); WS_STAMP(part, 6); WS_NOTE(part, 8, (unsigned long long)trace_rows); WS_NOTE(part, 9, 0ull); WS_NOTE(part, 10, (unsigned long long)chain); }
+        if (tid == 0) sm.part = next_ticket;
+        __syncthreads();
+
+        // ---- the next tile: its ticket has arrived; its keys travel during the write-out ------------------------------------
+        const uint32_t next_part = sm.part;
+        const bool more = next_part < total_tiles;
+        TileId nxt = cur;
+        if (more) {
+            nxt = locate(next_part);
+            load_keys(nxt);   // this tile's keys sit in shared memory by now: the registers are free
+        }
+
+        // ---- write-out: position i of the locally sorted tile goes to global_base[digit] + i (contiguous per bin) ---------
+        uint32_t pos[OUT_PAIRS ? SORT_KPT : 1];
+        if (full) {  // every tile but a segment's last: no per-key bounds branch
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_KPT; ++k) {
+                const uint32_t i = tid + k * SORT_THREADS;
+                const uint64_t kk = sm.keys[i];
+                const uint32_t p = sm.global_base[digit_out(kk)] + i;
+                if (OUT_PAIRS) pos[k] = p;
+                dst_keys[p] = kk;
             }
         } else {
 #pragma unroll
-            for (uint32_t k = 0; k < WS_KPT; ++k) {
-                const uint32_t i = tid + k * WS_GROUP_THREADS;
+            for (uint32_t k = 0; k < SORT_KPT; ++k) {
+                const uint32_t i = tid + k * SORT_THREADS;
                 if (i < n_valid) {
-                    const uint64_t kk = tile[i];
-                    dst_keys[sm.global_base[digit_of(kk)] + i] = kk;
+                    const uint64_t kk = sm.keys[i];
+                    const uint32_t p = sm.global_base[digit_out(kk)] + i;
+                    if (OUT_PAIRS) pos[k] = p;
+                    dst_keys[p] = kk;
                 }
             }
         }
-        // the buffer was written through the generic proxy (the scatter) and is about to be written by TMA (async proxy)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.raw_empty[b]);   // this buffer may receive the tile after next
         if (tid == 0) WS_STAMP(part, 7);
+        if (OUT_PAIRS) {
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_KPT; ++k) sm.vals[rank[k]] = val[k];
+            __syncthreads();
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_KPT; ++k) {
+                const uint32_t i = tid + k * SORT_THREADS;
+                if (i < n_valid) dst_vals[pos[k]] = sm.vals[i];
+            }
+        }
+        if (!more) break;
+        // the next tile's scatter and look-back overwrite sm.keys / sm.vals / sm.global_base: they come after its two
+        // barriers, which no thread passes before it has finished this write-out; sm.part is rewritten after them too
+        cur = nxt;
+        part = next_part;
     }
 }
-
-#endif  // TPDCU_SORT_WS
 
 // introspection: sorted words -> the reference's (tile << 32 | depth bits, index) arrays
 __global__ void sort_unpack_kernel(RasterLaunch a, uint64_t* out_keys, uint32_t* out_vals) {
@@ -1014,9 +644,10 @@ __global__ void sort_copy_result_kernel(const uint64_t* keys1, const uint32_t* v
     }
 }
 
+// upper bound of the tiles (= look-back descriptor rows, = CTAs) of a pass: every segment may end in a partial tile
 uint32_t sort_parts(uint32_t capacity, uint32_t kind) {
-    const uint32_t tile = kind == SORT_KIND_PAIRS ? SORT_TILE_PAIRS : SORT_TILE_WORDS;
-    return (capacity + tile - 1) / tile;
+    const uint32_t tile = tile_of(kind);
+    return (capacity + tile - 1) / tile + chains_of(kind);
 }
 uint32_t sort_passes_for(uint32_t end_bit) { return passes_needed(end_bit); }
 
@@ -1030,9 +661,6 @@ static cudaError_t set_smem_attr() {
 cudaError_t init_sort_attributes() {
     cudaError_t e = set_smem_attr<MODE_PAIRS>();
     if (e == cudaSuccess) e = set_smem_attr<MODE_WORDS>();
-#if TPDCU_SORT_WS
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(onesweep_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem));
-#endif
     return e;
 }
 
@@ -1047,24 +675,22 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     }
     const uint32_t chunk = HIST_THREADS * HIST_KPT;
     uint32_t hist_grid = (bound + chunk - 1) / chunk;
-    const uint32_t hist_max = (uint32_t)a.sm_count * 4u;
+    // every CTA adds up to passes x segments x 256 counters to the global histograms: few, fat CTAs
+    const uint32_t hist_max = (uint32_t)a.sm_count * (a.kind == SORT_KIND_DEPTH ? TPDCU_HIST_CTAS_DEPTH : TPDCU_HIST_CTAS_TILE);
     if (hist_grid > hist_max) hist_grid = hist_max;
     if (words) sort_hist_kernel<true><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
     else sort_hist_kernel<false><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
     if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
     const uint32_t parts = sort_parts(bound, a.kind);
     const uint32_t parts_cap = sort_parts(a.capacity, a.kind);
+    // the pass kernel is persistent: as many CTAs as stay resident, each drawing tiles by ticket until none is left
+    const uint32_t resident = (uint32_t)a.sm_count * (words ? TPDCU_SORT_MINB_WORDS : TPDCU_SORT_MINB) * TPDCU_SORT_GRID_FACTOR;
     for (uint32_t p = 0; p < num_passes; ++p) {
         uint32_t* lb = a.lookback + (size_t)p * parts_cap * SORT_BINS;
-#if TPDCU_SORT_WS
-        if (words)  // persistent: one CTA per SM (fewer when the buffer cannot hold that many tiles), tiles drawn by ticket
-            onesweep_ws_kernel<<<std::min<uint32_t>((uint32_t)a.sm_count, (parts + WS_GROUPS - 1) / WS_GROUPS), WS_THREADS, sizeof(WsSmem), s>>>(a.keys[0], a.keys[1], a.ctl, a.plan, lb, p);
-#else
         if (words)
-            onesweep_kernel<MODE_WORDS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<MODE_WORDS>), s>>>(a.keys[0], a.keys[1], nullptr, nullptr, a.ctl, a.plan, lb, p);
-#endif
+            onesweep_kernel<MODE_WORDS><<<std::min(parts, resident), SORT_THREADS, sizeof(OnesweepSmem<MODE_WORDS>), s>>>(a.keys[0], a.keys[1], nullptr, nullptr, a.ctl, a.plan, lb, p);
         else
-            onesweep_kernel<MODE_PAIRS><<<parts, SORT_THREADS, sizeof(OnesweepSmem<MODE_PAIRS>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
+            onesweep_kernel<MODE_PAIRS><<<std::min(parts, resident), SORT_THREADS, sizeof(OnesweepSmem<MODE_PAIRS>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
     }
     return cudaGetLastError();
 }
