@@ -768,7 +768,13 @@ int tpdcu_bind_output_fd(tpdcu_ctx* c, int fd, size_t bytes) {
     hd.size = bytes;
     hd.flags = cudaExternalMemoryDedicated;  // torpedo allocates targets with VMA's DEDICATED_MEMORY_BIT (VmaUsage.cpp:28-42)
     cudaExternalMemory_t mem;
-    CK(cudaImportExternalMemory(&mem, &hd));
+    cudaError_t ie = cudaImportExternalMemory(&mem, &hd);
+    if (ie != cudaSuccess) {  // an exporter whose allocation is not a dedicated one (a failed import leaves the fd with the caller)
+        cudaGetLastError();
+        hd.flags = 0;
+        ie = cudaImportExternalMemory(&mem, &hd);
+    }
+    CK(ie);
     cudaExternalMemoryBufferDesc bd{};
     bd.offset = 0;
     bd.size = bytes;
