@@ -120,12 +120,14 @@ def measured_peak_hbm():
 
 
 def ncu_traffic_per_launch():
-    """dram bytes per onesweep launch from the committed ncu capture summary, if there is one."""
+    """dram bytes per onesweep launch and where the figure comes from: the committed summary of one `ncu --set full` capture
+    (profiles/onesweep_traffic.json). bench.py cannot run under a profiler, so the number is NOT measured in this run."""
     try:
         with open(os.path.join(ROOT, "profiles", "onesweep_traffic.json")) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
+            d = json.load(f)
+            return float(d["dram_bytes_per_launch"]), d.get("source", "profiles/onesweep_traffic.json")
     except Exception:
-        return None
+        return None, None
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -374,6 +376,7 @@ def run_gpu(args):
         total_frames = K * world * rounds
         ms_per_frame = elapsed_ms / total_frames
         peak, peak_src = measured_peak_hbm()
+        traffic, traffic_src = ncu_traffic_per_launch()
         # dominant HBM-bound kernel of the sort: one onesweep pass over the pair words (8 B in + 8 B out per pair)
         passes = max(int(stages["tile_passes_run"]), 1)
         pass_ms = (stages["tile_sort"] - stages["tile_sort_hist_plan"]) / passes
@@ -405,7 +408,7 @@ def run_gpu(args):
                              "tile_sort": "hbm (onesweep passes) + smem atomics (histogram)", "ranges": "hbm", "blend": "SM issue + L1 gathers (on-demand SH colour inside)"},
             "roofline": {"kernel": "onesweep_kernel<WORDS> (one 8-bit digit pass of the tile sort over the pair words; average over the passes of a frame)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                         "traffic": ncu_traffic_per_launch(), "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pass_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pass_ms,
                          "peak_source": peak_src},
             "e2e": {"value": e2e_ms / e2e_steps / world, "unit": "ms/frame", "h2d_bytes_per_step": 136, "d2h_bytes_per_step": frame_bytes,
                     "steps": e2e_steps, "checksum": checksum, "serial_latency_ms": e2e_serial_ms / e2e_steps,
