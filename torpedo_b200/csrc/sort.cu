@@ -16,6 +16,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace tpdcu {
 
@@ -129,55 +130,65 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
     __syncthreads();
     // Each thread takes HIST_KPT CONSECUTIVE elements (two 32-byte loads): the pairs of one Gaussian are adjacent in the
     // unsorted buffer and usually share the upper tile bits, so run-length encoding the digits in registers removes most
-    // shared-memory atomics and nearly all same-address conflicts.
+    // shared-memory atomics and nearly all same-address conflicts. The loop is instruction-bound (ncu: issue slots 66 % busy,
+    // 75 instructions per key before this form), so a words sort works on the 32-bit key, the per-pass constants are hoisted,
+    // and all but the last chunk of the buffer take a path without per-element bounds.
+    using Key = typename std::conditional<WORDS, uint32_t, uint64_t>::type;
+    const uint32_t h_s = (uint32_t)__cvta_generic_to_shared(&h[0]);
     const uint32_t chunk = HIST_THREADS * HIST_KPT;
     const uint32_t chunks = (n + chunk - 1) / chunk, per_cta = (chunks + gridDim.x - 1) / gridDim.x;
     const uint32_t slice_end = min((uint64_t)n, (uint64_t)(blockIdx.x + 1) * per_cta * chunk);
+    const uint32_t chain_shift = 31u - __clz(SORT_BINS / chains);   // previous digit -> segment: d >> chain_shift
     for (uint64_t base64 = (uint64_t)blockIdx.x * per_cta * chunk; base64 < slice_end; base64 += chunk) {
-        const uint32_t base = (uint32_t)base64;
-        const uint32_t first = base + threadIdx.x * HIST_KPT;
-        uint64_t k[HIST_KPT];
-        if (first + HIST_KPT <= n) {
+        const uint32_t first = (uint32_t)base64 + threadIdx.x * HIST_KPT;
+        if (first >= n) continue;
+        Key k[HIST_KPT];
+        const uint32_t valid = min(HIST_KPT, n - first);
+        if (valid == HIST_KPT) {
 #pragma unroll
             for (uint32_t j = 0; j < HIST_KPT / 4; ++j) {
                 uint64_t v[4];
                 ldg256(keys + first + 4 * j, v);
-                k[4 * j] = v[0]; k[4 * j + 1] = v[1]; k[4 * j + 2] = v[2]; k[4 * j + 3] = v[3];
+#pragma unroll
+                for (uint32_t r = 0; r < 4; ++r) k[4 * j + r] = (Key)sort_key<WORDS>(v[r], sp.bias);
             }
         } else {
 #pragma unroll
-            for (uint32_t j = 0; j < HIST_KPT; ++j) k[j] = first + j < n ? keys[first + j] : 0ull;
+            for (uint32_t j = 0; j < HIST_KPT; ++j) k[j] = (Key)sort_key<WORDS>(keys[min(first + j, n - 1u)], sp.bias);  // the tail repeats the last key: run-length absorbs it, `valid` below cuts it off
         }
-        const uint32_t valid = first >= n ? 0u : min(HIST_KPT, n - first);
-        if (valid) {
+        // first-pass segment of the thread's elements: changes at most once inside its HIST_KPT consecutive positions
+        const uint32_t c_first = first / seg0;
+        const uint32_t c_change = chains > 1 ? (c_first + 1u) * seg0 - first : HIST_KPT;   // elements j >= c_change sit in the next segment
+        constexpr uint32_t MAX_P = WORDS ? SORT_WORD_PASSES : SORT_MAX_PASSES;
 #pragma unroll
-            for (uint32_t j = 0; j < HIST_KPT; ++j) k[j] = sort_key<WORDS>(k[j], sp.bias);
-            // first-pass segment of the thread's elements: changes at most once inside its HIST_KPT consecutive positions
-            const uint32_t c_first = first / seg0;
-            const uint32_t c_change = (c_first + 1u) * seg0 - first;   // elements j >= c_change sit in the next segment
-            for (uint32_t p = 0; p < num_passes; ++p) {
-                const uint32_t shift = p * SORT_RADIX_BITS, mask = pass_mask(p, sp.total_bits);
-                const uint32_t prev_shift = (p - 1u) * SORT_RADIX_BITS, prev_mask = p ? pass_mask(p - 1u, sp.total_bits) : 0u;
-                auto slot = [&](uint32_t j) {
-                    const uint32_t d = (uint32_t)(k[j] >> shift) & mask;
-                    uint32_t c = 0;
-                    if (chains > 1) c = p == 0 ? c_first + (j >= c_change ? 1u : 0u) : ((uint32_t)(k[j] >> prev_shift) & prev_mask) / SORT_CHAIN_BINS;
-                    return (p * chains + c) * SORT_BINS + hist_slot(d);   // bank swizzle: the tile sort's low digits sit at stride 4
-                };
+        for (uint32_t p = 0; p < MAX_P; ++p) {   // unrolled: shifts and the first-pass case become immediates / straight code
+            if (p >= num_passes) break;
+            const uint32_t shift = p * SORT_RADIX_BITS, mask = pass_mask(p, sp.total_bits);
+            const uint32_t row_base = p * chains * SORT_BINS;
+            // slot of element j: row (pass, segment) * 256 + swizzled digit. Segment: position for the first pass, the previous
+            // digit for the others — for those, the bits above chain_shift of the previous digit, moved to bit 8.
+            const uint32_t seg_shift = (p - 1u) * SORT_RADIX_BITS + chain_shift;
+            const uint32_t seg_mask = p && chains > 1 ? (pass_mask(p - 1u, sp.total_bits) >> chain_shift) : 0u;
+            auto slot = [&](uint32_t j) {
+                const uint32_t d = (uint32_t)(k[j] >> shift) & mask;
+                const uint32_t c = p == 0 ? (chains > 1 ? c_first + (j >= c_change ? 1u : 0u) : 0u) : ((uint32_t)(k[j] >> seg_shift) & seg_mask);
+                return row_base + (c << SORT_RADIX_BITS) + hist_slot(d);   // bank swizzle: the tile sort's low digits sit at stride 4
+            };
+            if (valid == HIST_KPT) {
+                // run-length encode the eight slots; a run is flushed by ONE predicated shared-memory reduction (no branch:
+                // the compiler's divergent-branch form of `if (changed) atomicAdd` cost 4 of 22 instructions per key and pass)
                 uint32_t run_slot = slot(0), run = 1;
 #pragma unroll
                 for (uint32_t j = 1; j < HIST_KPT; ++j) {
-                    if (j < valid) {
-                        const uint32_t sl = slot(j);
-                        if (sl != run_slot) {
-                            atomicAdd(&h[run_slot], run);
-                            run_slot = sl;
-                            run = 0;
-                        }
-                        ++run;
-                    }
+                    const uint32_t sl = slot(j);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, %1;\n\t@p red.shared.add.u32 [%2], %3;\n\t}"
+                                 : : "r"(sl), "r"(run_slot), "r"(h_s + 4u * run_slot), "r"(run) : "memory");
+                    run = (sl != run_slot ? 0u : run) + 1u;
+                    run_slot = sl;
                 }
-                atomicAdd(&h[run_slot], run);
+                asm volatile("red.shared.add.u32 [%0], %1;" : : "r"(h_s + 4u * run_slot), "r"(run) : "memory");
+            } else {
+                for (uint32_t j = 0; j < valid; ++j) atomicAdd(&h[slot(j)], 1u);   // only the buffer's last thread
             }
         }
     }
@@ -216,16 +227,22 @@ __device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, S
     const bool owner = b < SORT_BINS;
     if (b < SORT_MAX_PASSES) s_skip[b] = 0;
     __syncthreads();
+    // per bin: the segments' counts become the exclusive sum over the segments before them; their total is the bin's count.
+    // All loads first (independent, one round trip), then the sums: the plan is a serial tail behind the histogram kernel.
+    uint32_t seg_count[SORT_CHAIN_ROWS];
+    const uint32_t rows = num_passes * chains;
+#pragma unroll
+    for (uint32_t r = 0; r < SORT_CHAIN_ROWS; ++r) seg_count[r] = (owner && r < rows) ? ld_relaxed_u32(&ctl->chain_hist[r][b]) : 0u;
+    __shared__ uint32_t s_bin_start[SORT_MAX_PASSES][SORT_CHAINS + 1];   // exclusive offset of the first bin of every segment
     for (uint32_t p = 0; p < num_passes; ++p) {
-        // per bin: the segments' counts become the exclusive sum over the segments before them; their total is the bin's count
         uint32_t c = 0;
-        if (owner)
-            for (uint32_t ch = 0; ch < chains; ++ch) {
-                uint32_t* cell = &ctl->chain_hist[p * chains + ch][b];
-                const uint32_t v = ld_relaxed_u32(cell);
-                *cell = c;
-                c += v;
+#pragma unroll
+        for (uint32_t r = 0; r < SORT_CHAIN_ROWS; ++r) {
+            if (owner && r >= p * chains && r < (p + 1) * chains) {
+                ctl->chain_hist[r][b] = c;
+                c += seg_count[r];
             }
+        }
         if (owner && c == n) s_skip[p] = 1;  // every key falls in this bin (also true for n == 0)
         uint32_t incl = c;
 #pragma unroll
@@ -238,7 +255,9 @@ __device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, S
         if (owner) {
             uint32_t wex = 0;
             for (uint32_t w = 0; w < warp; ++w) wex += s_warp[w];
-            ctl->hist[p][b] = wex + incl - c;
+            const uint32_t start = wex + incl - c;
+            ctl->hist[p][b] = start;
+            if (b % (SORT_BINS / chains) == 0) s_bin_start[p][b / (SORT_BINS / chains)] = start;
         }
         __syncthreads();
     }
@@ -265,7 +284,7 @@ __device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, S
             uint32_t rows = 0;
             for (uint32_t ch = 0; ch <= SORT_CHAINS; ++ch) {
                 uint32_t start = n;
-                if (ch < chains) start = p == 0 ? (uint32_t)min((uint64_t)n, (uint64_t)ch * seg0) : ctl->hist[p - 1][ch * (SORT_BINS / chains)];
+                if (ch < chains) start = p == 0 ? (uint32_t)min((uint64_t)n, (uint64_t)ch * seg0) : s_bin_start[p - 1][ch];
                 plan->seg_start[p][ch] = start;
             }
             for (uint32_t ch = 0; ch <= SORT_CHAINS; ++ch) {
