@@ -42,6 +42,9 @@ constexpr uint32_t LOOKBACK_BATCH = TPDCU_LOOKBACK_BATCH;
 #ifndef TPDCU_SORT_DRAW_EARLY
 #define TPDCU_SORT_DRAW_EARLY 1          // 1: the next ticket is drawn before the ranking instead of after it
 #endif
+#ifndef TPDCU_SORT_LOAD_EARLY
+#define TPDCU_SORT_LOAD_EARLY 0          // the next tile's key loads are issued before the look-back (needs DRAW_EARLY)
+#endif
 #ifndef TPDCU_SORT_RANK_BATCH
 #define TPDCU_SORT_RANK_BATCH 8          // ranking atomics in flight per thread before their keys are scattered
 #endif
@@ -552,6 +555,18 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
 #if !TPDCU_SORT_DRAW_EARLY
         if (tid == 0) next_ticket = atomicAdd(&ctl->ticket[pass], 1u);   // travels while this tile's look-back runs
 #endif
+#if TPDCU_SORT_DRAW_EARLY && TPDCU_SORT_LOAD_EARLY
+        // ---- the next tile: its ticket arrived during the ranking; its keys travel during the look-back and the write-out ------
+        if (tid == 0) sm.part = next_ticket;
+        __syncthreads();   // also: every key of this tile is in shared memory, the key registers are free
+        const uint32_t next_part = sm.part;
+        const bool more = next_part < total_tiles;
+        TileId nxt = cur;
+        if (more) {
+            nxt = locate(next_part);
+            load_keys(nxt);
+        }
+#endif
         if (tid == 0) { WS_STAMP(part, 3); WS_STAMP(part, 5); }
 
         // ---- decoupled look-back, one thread per bin -----------------------------------------------------
@@ -586,6 +601,9 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         // bin's output run + keys of the earlier segments in that bin + keys of this segment's earlier tiles - tile-local offset
         sm.global_base[tid] = ctl->hist[pass][tid] + ctl->chain_hist[pass * chains + chain][tid] + excl - bin_base;
         if (tid == 0) { WS_STAMP(part, 4); WS_STAMP(part, 6); WS_NOTE(part, 8, (unsigned long long)trace_rows); WS_NOTE(part, 9, 0ull); WS_NOTE(part, 10, (unsigned long long)chain); }
+#if TPDCU_SORT_DRAW_EARLY && TPDCU_SORT_LOAD_EARLY
+        __syncthreads();
+#else
         if (tid == 0) sm.part = next_ticket;
         __syncthreads();
 
@@ -597,6 +615,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
             nxt = locate(next_part);
             load_keys(nxt);   // this tile's keys sit in shared memory by now: the registers are free
         }
+#endif
 
         // ---- write-out: position i of the locally sorted tile goes to global_base[digit] + i (contiguous per bin) ---------
         uint32_t pos[OUT_PAIRS ? SORT_KPT : 1];
