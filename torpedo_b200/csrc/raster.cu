@@ -233,6 +233,20 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
     float T0 = 1.0f, T1 = 1.0f, r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
 
     uint32_t in = range.x;
+    // Software pipeline of the staging loads. A round's candidates are reached through two dependent gathers (sorted word ->
+    // SplatGeo record) before the cull, and the survivors through a third (position + SH row) before the colour; with all
+    // three issued inside the round every fill exposed three memory latencies (ncu: 36 % of the kernel's stall samples on
+    // them, 16 % more on the barriers behind them). The words are fetched two rounds ahead and the SplatGeo records one round
+    // ahead — both right after the cull of the current round, so they travel during its colour evaluation and its drain —
+    // and a round only waits for the gather that depends on the cull: the survivors' rows. (Measured and discarded for
+    // those: one cp.async.bulk per survivor into shared memory behind a per-warp mbarrier — 128 small TMA copies per round
+    // are no faster than the loads and cost a CTA per SM in shared memory (0.349 ms); the SH degree as a template parameter
+    // (0.353 ms); prefetch.global.L2 of the survivors' rows at cull time (0.373 ms against 0.342 ms).)
+    uint32_t g_cur = 0, g_next = 0;
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+    if (in + tid < range.y) g_cur = (uint32_t)__ldg(words + in + tid);
+    if (in + BLEND_THREADS + tid < range.y) g_next = (uint32_t)__ldg(words + in + BLEND_THREADS + tid);
+    if (in + tid < range.y) ldg256(geo4 + (size_t)g_cur * 2, ra, rb);  // the 32-byte SplatGeo record: one sector, one load
     while (true) {
         // ---- fill: append the next splats that can touch this tile / each quadrant, in order --------------------------
         uint32_t qn = 0;                                // queue entries
@@ -240,11 +254,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
         while (qn + BLEND_THREADS <= BLEND_QUEUE && in < range.y) {
             const uint32_t idx = in + tid;
             uint32_t keep = 0;  // bit 0: tile, bits 1..4: quadrants 0..3
-            uint32_t g = 0;
-            float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+            const uint32_t g = g_cur;
             if (idx < range.y) {
-                g = (uint32_t)__ldg(words + idx);
-                ldg256(geo4 + (size_t)g * 2, ra, rb);  // the 32-byte SplatGeo record: one sector, one load
                 const float xlo = ra.x - rb.z - tile_fx0, xhi = ra.x + rb.z - tile_fx0;  // bbox relative to the tile origin
                 const float ylo = ra.y - rb.w - tile_fy0, yhi = ra.y + rb.w - tile_fy0;
                 const bool left = xhi >= 0.0f && xlo <= 7.0f, right = xhi >= 8.0f && xlo <= 15.0f;
@@ -259,6 +270,11 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
                 ballot[q] = __ballot_sync(0xffffffffu, (keep >> q) & 1u);
                 if (lane == q) sm.cnt[warp][q] = __popc(ballot[q]);
             }
+            // the next round's SplatGeo record (its word arrived a round ago) and the word of the round after it
+            float4 ra_n = make_float4(0.f, 0.f, 0.f, 0.f), rb_n = ra_n;
+            uint32_t g_next2 = 0;
+            if (idx + BLEND_THREADS < range.y) ldg256(geo4 + (size_t)g_next * 2, ra_n, rb_n);
+            if (idx + 2 * BLEND_THREADS < range.y) g_next2 = (uint32_t)__ldg(words + idx + 2 * BLEND_THREADS);
             __syncthreads();
             uint32_t before[BLEND_WARPS + 1], total[BLEND_WARPS + 1];
 #pragma unroll
@@ -280,19 +296,19 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
                 // the HBM roofline: 1.2 GB per frame, 0.19 ms; here 0.56 GB are gathered inside a kernel that is not
                 // memory-bound). Same arithmetic as the introspection kernel (common.cuh: sh_basis / sh_accumulate).
                 const float4 po = __ldg(a.posop + g);
-                const float3 c3 = sh_color(a.sh + (size_t)g * SH_PLANES, po.x, po.y, po.z, cam_pos, (int)a.sh_degree);
-                const float4 col = make_float4(c3.x, c3.y, c3.z, 0.0f);
                 sm.ent[pos].g0 = make_float4(ra.x, ra.y, (-0.5f * LOG2E) * ra.z, -LOG2E * ra.w);
                 sm.ent[pos].g1 = make_float4((-0.5f * LOG2E) * rb.x, rb.y, -__log2f(255.0f * rb.y) - 0.01f, 0.0f);
-                sm.ent[pos].col = col;
 #pragma unroll
                 for (uint32_t q = 0; q < BLEND_WARPS; ++q)
                     if (keep & (2u << q)) sm.list[q][ln[q] + before[q + 1] + __popc(ballot[q + 1] & lanemask_lt())] = (uint16_t)(pos * sizeof(BlendEntry));
+                const float3 c3 = sh_color(a.sh + (size_t)g * SH_PLANES, po.x, po.y, po.z, cam_pos, (int)a.sh_degree);
+                sm.ent[pos].col = make_float4(c3.x, c3.y, c3.z, 0.0f);
             }
             qn += total[0];
 #pragma unroll
             for (uint32_t q = 0; q < BLEND_WARPS; ++q) ln[q] += total[q + 1];
             in += BLEND_THREADS;
+            g_cur = g_next; g_next = g_next2; ra = ra_n; rb = rb_n;
             __syncthreads();
         }
 
