@@ -458,15 +458,25 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev):
         ubos.append(cam.pack())
     ubos = np.stack(ubos)
 
+    from torpedo_b200._lib import check, tpdcu
+    lib = tpdcu()
+
     def render_batch(view_ids, out):
-        eng.raster_views(ubos[list(view_ids)], out.data_ptr(), HEIGHT * WIDTH * 4, SH_DEGREE, stream)
+        # asynchronous: every view is enqueued behind the previous one (three frames in flight inside the engine) and the
+        # gather of a chunk is ordered behind its frames on the stream; the host only waits at the end of the batch
+        for k, v in enumerate(view_ids):
+            check(lib.tpdcu_bind_output_device_ptr(eng.ctx, out[k].data_ptr(), WIDTH * 4))
+            eng.raster_ubo(ubos[v], SH_DEGREE, stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(2):                                   # warm-up: pair buffers grow to the batch's largest view
+    for v in range(rank, views, world):                  # warm-up: pair buffers grow to the largest view of this rank
+        eng.raster_ubo(ubos[v], SH_DEGREE, stream)
+        eng.finish()
+    for _ in range(2):
         mv.render_views(render_batch, views, HEIGHT, WIDTH, dev, chunk=chunk)
         eng.finish()
     repeats_before = eng.frames_repeated()
