@@ -66,7 +66,7 @@ struct FrameCtl {
     uint32_t visible;                     // Gaussians with tiles > 0
     uint32_t depth_max;                   // max float bits of viewZ over the visible Gaussians (atomicMax)
     uint32_t inv_depth_min;               // ~min float bits (atomicMax on the complement, so zero-init works)
-    uint32_t pad0[2];
+    unsigned long long pairs64;           // P again, summed in 64 bits per partition: the packed scan carries at 2^32 (host-side check)
     SortCtl depth_sort;                   // visible Gaussians by view depth
     SortCtl tile_sort;                    // (tile, Gaussian) pairs by tile; also the standalone pair sort
 };
@@ -383,6 +383,7 @@ struct RasterLaunch {
     uint8_t* out;
     size_t pitch;
     uint32_t width, height;
+    int sm_count;
 };
 cudaError_t launch_ranges(const RasterLaunch& a, uint32_t capacity, cudaStream_t s);
 cudaError_t launch_blend(const RasterLaunch& a, cudaStream_t s);

@@ -294,7 +294,9 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
                     pr[b0 + k] = project_one(a, i, po[k], ca[k], cb[k], s_vm, s_pm, s_v, s_focal, gx, gy);
                 } else {
                     float vm_l[16], pm_l[16];
-                    const uint32_t e = __ldg(a.scene.entity + i);
+                    // an index past the entity table (only possible through tpdcu_upload_gaussians_device, whose indices are
+                    // not validated on the host) must not read outside the matrices
+                    const uint32_t e = min(__ldg(a.scene.entity + i), a.scene.entity_count - 1u);
 #pragma unroll
                     for (int q = 0; q < 16; ++q) { vm_l[q] = __ldg(a.vm + e * 16 + q); pm_l[q] = __ldg(a.pm + e * 16 + q); }
                     pr[b0 + k] = project_one(a, i, po[k], ca[k], cb[k], vm_l, pm_l, s_v, s_focal, gx, gy);
@@ -356,6 +358,9 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
         }
         if (lane == 0) {
             s_base = exclusive;
+            // the packed (visible | pairs) scan carries into the visible count once P reaches 2^32: keep an exact 64-bit P
+            // beside it, so that the host can refuse such a frame instead of trusting a wrapped count
+            atomicAdd(&a.ctl->pairs64, (unsigned long long)(uint32_t)total);
             if (part == num_parts - 1) {
                 const uint64_t all = exclusive + total;
                 a.ctl->pairs_total = (uint32_t)all;

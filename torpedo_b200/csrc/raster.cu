@@ -130,7 +130,8 @@ cudaError_t launch_ranges(const RasterLaunch& a, uint32_t capacity, cudaStream_t
     const uint32_t tiles = ((a.width + TILE_PX - 1) / TILE_PX) * ((a.height + TILE_PX - 1) / TILE_PX);
     if (capacity != 0) {
         uint32_t grid = (capacity / 4 + 256) / 256;
-        if (grid > 148u * 8u) grid = 148u * 8u;
+        const uint32_t cap = (uint32_t)(a.sm_count > 0 ? a.sm_count : 148) * 8u;
+        if (grid > cap) grid = cap;
         ranges_kernel<<<grid, 256, 0, s>>>(a);
     }
     if (tiles != 0) tile_order_kernel<<<1, ORDER_THREADS, 0, s>>>(a, tiles);

@@ -49,6 +49,7 @@ static_assert(offsetof(SortPlan, total_bits) == 5 * sizeof(uint32_t), "PlanHead 
 struct FrameStatus {  // pinned host mirror of what a frame reports back
     uint32_t pairs_total;
     uint32_t visible;
+    unsigned long long pairs64;
     PlanHead tile, depth;
 };
 
@@ -401,7 +402,7 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
     ra.order = ra.ranges + 2 * (size_t)tiles_of(c);
     ra.tile_cost = c->tile_cost;
     ra.posop = c->posop; ra.sh = c->sh; ra.cam = f.cam; ra.sh_degree = l.pre.sh_degree;
-    ra.out = tk.out; ra.pitch = tk.pitch; ra.width = c->width; ra.height = c->height;
+    ra.out = tk.out; ra.pitch = tk.pitch; ra.width = c->width; ra.height = c->height; ra.sm_count = c->sm_count;
 
     if (t) CK(cudaEventRecord(c->ev[0], s));
     CameraUbo cu;
@@ -463,6 +464,7 @@ static int enqueue_frame(tpdcu_ctx* c, FrameSlot& f, FrameTicket& tk) {
 
     FrameStatus* st = &c->status[tk.status];
     CK(cudaMemcpyAsync(&st->pairs_total, &ctl->pairs_total, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&st->pairs64, &ctl->pairs64, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&st->tile, f.plan, sizeof(PlanHead), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&st->depth, f.depth_plan, sizeof(PlanHead), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(f.done, s));
@@ -540,6 +542,8 @@ static int finish_internal(tpdcu_ctx* c) {
         size_t first_overflow = pending.size();
         for (size_t i = 0; i < pending.size(); ++i) {
             const FrameStatus& st = c->status[pending[i].status];
+            if (st.pairs64 >= 0xffffffffull - 2ull * SORT_TILE)
+                return fail(TPDCU_ERR_INVALID, "a frame produced " + std::to_string(st.pairs64) + " (tile, Gaussian) pairs: the pair buffers hold fewer than 2^32");
             if (st.pairs_total <= pending[i].ran_capacity) continue;
             max_pairs = std::max(max_pairs, st.pairs_total);
             first_overflow = std::min(first_overflow, i);
@@ -669,22 +673,43 @@ int tpdcu_device_info(tpdcu_ctx* c, char* buf, size_t buf_bytes, int* sm_count) 
 
 static int upload_common(tpdcu_ctx* c, const void* d_recs, uint32_t n, const uint32_t* d_entity, uint32_t entity_count,
                          cudaStream_t s) {
+    // The new scene is allocated BESIDE the old one and only then swapped in, so that a failed compile() leaves the engine
+    // with the scene it had; if the two do not fit together the old one is dropped first (and a failure then leaves none).
+    float4 *posop = nullptr, *cov_a = nullptr, *sh = nullptr;
+    float2* cov_b = nullptr;
+    uint32_t* entity = nullptr;
+    auto alloc_all = [&]() -> cudaError_t {
+        cudaError_t e = cudaMalloc(&posop, (size_t)n * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc(&cov_a, (size_t)n * sizeof(float4));
+        if (e == cudaSuccess) e = cudaMalloc(&cov_b, (size_t)n * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc(&sh, (size_t)n * SH_PLANES * sizeof(float4));
+        if (e == cudaSuccess && entity_count > 1) e = cudaMalloc(&entity, (size_t)n * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(posop); cudaFree(cov_a); cudaFree(cov_b); cudaFree(sh); cudaFree(entity);
+            posop = cov_a = sh = nullptr; cov_b = nullptr; entity = nullptr;
+        }
+        return e;
+    };
+    cudaError_t e = alloc_all();
+    if (e == cudaErrorMemoryAllocation && c->n != 0) {
+        free_scene(c);
+        forget_frames(c);
+        e = alloc_all();
+    }
+    CK(e);
     free_scene(c);
     forget_frames(c);
-    CK(cudaMalloc(&c->posop, (size_t)n * sizeof(float4)));
-    CK(cudaMalloc(&c->cov_a, (size_t)n * sizeof(float4)));
-    CK(cudaMalloc(&c->cov_b, (size_t)n * sizeof(float2)));
-    CK(cudaMalloc(&c->sh, (size_t)n * SH_PLANES * sizeof(float4)));
+    c->posop = posop; c->cov_a = cov_a; c->cov_b = cov_b; c->sh = sh; c->entity = entity;
     if (entity_count > 1) {
-        CK(cudaMalloc(&c->entity, (size_t)n * sizeof(uint32_t)));
         if (d_entity) CK(cudaMemcpyAsync(c->entity, d_entity, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
         else CK(cudaMemsetAsync(c->entity, 0, (size_t)n * sizeof(uint32_t), s));
     }
     c->n = n;
     c->entity_count = entity_count;
     c->models_host.assign((size_t)entity_count * 16, 0.0f);  // identity (createBindlessTransformBuffer)
-    for (uint32_t e = 0; e < entity_count; ++e)
-        for (int k = 0; k < 4; ++k) c->models_host[(size_t)e * 16 + k * 5] = 1.0f;
+    for (uint32_t e2 = 0; e2 < entity_count; ++e2)
+        for (int k = 0; k < 4; ++k) c->models_host[(size_t)e2 * 16 + k * 5] = 1.0f;
     ++c->models_version;
     CompileLaunch cl{ reinterpret_cast<const float*>(d_recs), c->posop, c->cov_a, c->cov_b, c->sh, n };
     CK(launch_compile_scene(cl, s));
