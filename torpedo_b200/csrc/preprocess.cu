@@ -12,6 +12,8 @@
 //   GaussianEngine.cpp:662-674 (the mid-frame fence wait + read of tilesRendered is gone)
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace tpdcu {
 
 // ---------------------------------------------------------------------------------------------------
@@ -248,11 +250,26 @@ __device__ __forceinline__ Projected project_one(const PreprocessLaunch& a, uint
 // Besides the per-Gaussian records it compacts the visible Gaussians, in index order, into `depth_words`
 // (float_bits(viewZ) << 32 | index): the input of the depth sort. The (visible, pairs) scan also yields the reference's
 // pair offsets (prefix.slang) and P.
-__global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLaunch a) {
+#ifndef TPDCU_PRE_MINB
+#define TPDCU_PRE_MINB 4
+#endif
+// A resident CTA works through partitions of PRE_PART consecutive Gaussians (PRE_ITEMS per thread, striped so that loads
+// coalesce), one ticket at a time. Besides the per-Gaussian records it compacts the visible Gaussians, in index order, into
+// `depth_words` (float_bits(viewZ) << 32 | index): the input of the depth sort. The (visible, pairs) scan also yields the
+// reference's pair offsets (prefix.slang) and P.
+//
+// The look-back of a partition is DEFERRED behind the geometry of the CTA's next partition. A partition's geometry takes
+// 2-10 us depending on how many of its Gaussians survive the culls, and with one partition per CTA every CTA sat on its SM
+// slot until the slowest of its 32 predecessors had published an aggregate (ncu: 35 % of all stall samples behind that
+// barrier, 121 polls of the descriptor window per partition). Now the aggregate is published as soon as it is known, the CTA
+// goes on with the next partition, and only then resolves the previous one's prefix: every predecessor has published by then,
+// and as every CTA defers alike the distance to the nearest PREFIX stays what it was.
+__global__ void __launch_bounds__(PRE_THREADS, TPDCU_PRE_MINB) preprocess_kernel(PreprocessLaunch a) {
     __shared__ uint32_t s_part;
-    __shared__ uint64_t s_base;                 // exclusive (visible, pairs) prefix of this partition
+    __shared__ uint64_t s_base;                 // exclusive (visible, pairs) prefix of the partition being completed
     __shared__ float s_vm[16], s_pm[16], s_v[12], s_focal[2];
-    __shared__ uint64_t s_warp_tot[PRE_ITEMS][PRE_THREADS / 32];
+    __shared__ uint64_t s_warp_tot[2][PRE_ITEMS][PRE_THREADS / 32];   // [parity of the partition's turn in this CTA]
+    __shared__ uint64_t s_total[2];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_part = atomicAdd(&a.ctl->scan_ticket, 1u);
@@ -263,131 +280,164 @@ __global__ void __launch_bounds__(PRE_THREADS, 4) preprocess_kernel(PreprocessLa
         if (tid < 2) s_focal[tid] = a.cam->focal[tid];
     }
     __syncthreads();
-    const uint32_t part = s_part;
     const uint32_t n = a.scene.n;
-    const uint32_t first = part * PRE_PART + tid;
+    const uint32_t num_parts = (n + PRE_PART - 1) / PRE_PART;
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX, gy = (a.height + TILE_PX - 1) / TILE_PX;
+    uint32_t part = s_part;
 
-    // ---- geometry, in batches of PRE_BATCH Gaussians per thread: all loads of a batch first, then its arithmetic. Only the
-    // tile count and the depth bits of a Gaussian stay in registers (project_one stores the records), so a partition can
-    // hold several batches: fewer partitions = fewer look-backs and less waiting on them per Gaussian.
-    Projected pr[PRE_ITEMS];
-#pragma unroll
-    for (uint32_t b0 = 0; b0 < PRE_ITEMS; b0 += PRE_BATCH) {
-        float4 po[PRE_BATCH], ca[PRE_BATCH];
-        float2 cb[PRE_BATCH];
-#pragma unroll
-        for (uint32_t k = 0; k < PRE_BATCH; ++k) {
-            const uint32_t i = first + (b0 + k) * PRE_THREADS;
-            if (i < n) {
-                po[k] = __ldg(a.scene.posop + i);
-                ca[k] = __ldg(a.scene.cov_a + i);
-                cb[k] = __ldg(a.scene.cov_b + i);
+    // what a partition leaves behind for its completion, one turn later: per Gaussian its tile count, its depth bits and the
+    // exclusive (visible, pairs) prefix inside its warp's group — parked in shared memory, the registers belong to the geometry
+    __shared__ uint4 s_stash[2][PRE_ITEMS][PRE_THREADS];
+    uint32_t prev_part = 0xffffffffu, prev_par = 0;
+
+    // completion of partition `prev_part` (its turn had parity `par`): look-back, then the prefix-dependent stores
+    auto complete = [&](uint32_t par) {
+        if (warp == 0) {
+            const uint64_t total = s_total[par];
+            uint64_t exclusive = 0;
+            if (prev_part != 0) {
+                exclusive = lookback_exclusive(a.scan_desc, prev_part, lane);
+                if (lane == 0) st_relaxed_u64(a.scan_desc + prev_part, ((uint64_t)FLAG_PREFIX << 62) | (exclusive + total));
             }
-        }
-#pragma unroll
-        for (uint32_t k = 0; k < PRE_BATCH; ++k) {
-            const uint32_t i = first + (b0 + k) * PRE_THREADS;
-            pr[b0 + k] = Projected{ 0u, 0u };
-            if (i < n) {
-                if (single_entity) {
-                    pr[b0 + k] = project_one(a, i, po[k], ca[k], cb[k], s_vm, s_pm, s_v, s_focal, gx, gy);
-                } else {
-                    float vm_l[16], pm_l[16];
-                    // an index past the entity table (only possible through tpdcu_upload_gaussians_device, whose indices are
-                    // not validated on the host) must not read outside the matrices
-                    const uint32_t e = min(__ldg(a.scene.entity + i), a.scene.entity_count - 1u);
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) { vm_l[q] = __ldg(a.vm + e * 16 + q); pm_l[q] = __ldg(a.pm + e * 16 + q); }
-                    pr[b0 + k] = project_one(a, i, po[k], ca[k], cb[k], vm_l, pm_l, s_v, s_focal, gx, gy);
+            if (lane == 0) {
+                s_base = exclusive;
+                if (prev_part == num_parts - 1) {
+                    const uint64_t all = exclusive + total;
+                    a.ctl->pairs_total = (uint32_t)all;
+                    a.ctl->visible = (uint32_t)(all >> 32);
+                    a.out.offsets[n] = (uint32_t)all;
                 }
             }
         }
-    }
-
-    // ---- depth range of the frame (the depth sort only sorts the bits this range occupies, sort.cu sort_spec) ---------
-    {
-        uint32_t dmin = 0xffffffffu, dmax = 0u;
+        __syncthreads();
+        const uint64_t base = s_base;
+        const uint32_t first = prev_part * PRE_PART + tid;
 #pragma unroll
-        for (uint32_t k = 0; k < PRE_ITEMS; ++k)
-            if (pr[k].count != 0) { dmin = min(dmin, pr[k].depth_bits); dmax = max(dmax, pr[k].depth_bits); }
-        dmin = __reduce_min_sync(0xffffffffu, dmin);
-        dmax = __reduce_max_sync(0xffffffffu, dmax);
-        if (lane == 0 && dmax >= dmin) {  // after the first partitions the range rarely widens: test before the atomic
-            if (dmax > ld_relaxed_u32(&a.ctl->depth_max)) atomicMax(&a.ctl->depth_max, dmax);
-            if (~dmin > ld_relaxed_u32(&a.ctl->inv_depth_min)) atomicMax(&a.ctl->inv_depth_min, ~dmin);
-        }
-    }
-
-    // ---- partition-local exclusive scan of (visible, pairs); group k = Gaussians [k*256, (k+1)*256) of the partition ----
-    uint64_t mine[PRE_ITEMS], incl[PRE_ITEMS];
-#pragma unroll
-    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
-        mine[k] = ((uint64_t)(pr[k].count != 0) << 32) | pr[k].count;
-        incl[k] = mine[k];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint64_t up = __shfl_up_sync(0xffffffffu, incl[k], d);
-            if (lane >= (uint32_t)d) incl[k] += up;
-        }
-        if (lane == 31) s_warp_tot[k][warp] = incl[k];
-    }
-    __syncthreads();
-
-    // ---- warp 0: exclusive scan of the PRE_ITEMS x 8 (group, warp) totals (group-major: the order of the Gaussians), then
-    // the decoupled look-back across partitions ----------------------------------------------------------------------
-    const uint32_t num_parts = (n + PRE_PART - 1) / PRE_PART;
-    if (warp == 0) {
-        static_assert(PRE_ITEMS * (PRE_THREADS / 32) == 32, "one lane per (group, warp) total");
-        const uint64_t mine_tot = (&s_warp_tot[0][0])[lane];
-        uint64_t incl_tot = mine_tot;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint64_t up = __shfl_up_sync(0xffffffffu, incl_tot, d);
-            if (lane >= (uint32_t)d) incl_tot += up;
-        }
-        (&s_warp_tot[0][0])[lane] = incl_tot - mine_tot;  // exclusive prefix of this (group, warp) inside the partition
-        const uint64_t total = __shfl_sync(0xffffffffu, incl_tot, 31);
-        uint64_t exclusive = 0;
-        if (part == 0) {
-            if (lane == 0) st_relaxed_u64(a.scan_desc, ((uint64_t)FLAG_PREFIX << 62) | total);
-        } else {
-            if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_AGGREGATE << 62) | total);
-            exclusive = lookback_exclusive(a.scan_desc, part, lane);
-            if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_PREFIX << 62) | (exclusive + total));
-        }
-        if (lane == 0) {
-            s_base = exclusive;
-            // the packed (visible | pairs) scan carries into the visible count once P reaches 2^32: keep an exact 64-bit P
-            // beside it, so that the host can refuse such a frame instead of trusting a wrapped count
-            atomicAdd(&a.ctl->pairs64, (unsigned long long)(uint32_t)total);
-            if (part == num_parts - 1) {
-                const uint64_t all = exclusive + total;
-                a.ctl->pairs_total = (uint32_t)all;
-                a.ctl->visible = (uint32_t)(all >> 32);
-                a.out.offsets[n] = (uint32_t)all;
+        for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
+            const uint32_t i = first + k * PRE_THREADS;
+            if (i < n) {
+                const uint4 st = s_stash[par][k][tid];
+                const uint64_t at = base + s_warp_tot[par][k][warp] + (((uint64_t)st.w << 32) | st.z);
+                a.out.offsets[i] = (uint32_t)at;
+                if (st.x != 0) a.depth_words[(uint32_t)(at >> 32)] = ((uint64_t)st.y << 32) | i;
             }
         }
-    }
-    __syncthreads();
-    uint64_t local_excl[PRE_ITEMS];
+    };
+
+    for (uint32_t turn = 0; part < num_parts; ++turn) {
+        const uint32_t par = turn & 1u;
+        const uint32_t first = part * PRE_PART + tid;
+
+        // ---- geometry, in batches of PRE_BATCH Gaussians per thread: all loads of a batch first, then its arithmetic. Only
+        // the tile count and the depth bits of a Gaussian stay in registers (project_one stores the records).
+        Projected pr[PRE_ITEMS];
 #pragma unroll
-    for (uint32_t k = 0; k < PRE_ITEMS; ++k) local_excl[k] = s_warp_tot[k][warp] + incl[k] - mine[k];
-    const uint64_t base = s_base;
+        for (uint32_t b0 = 0; b0 < PRE_ITEMS; b0 += PRE_BATCH) {
+            float4 po[PRE_BATCH], ca[PRE_BATCH];
+            float2 cb[PRE_BATCH];
 #pragma unroll
-    for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
-        const uint32_t i = first + k * PRE_THREADS;
-        if (i < n) {
-            const uint64_t at = base + local_excl[k];
-            a.out.offsets[i] = (uint32_t)at;
-            if (pr[k].count != 0) a.depth_words[(uint32_t)(at >> 32)] = ((uint64_t)pr[k].depth_bits << 32) | i;
+            for (uint32_t k = 0; k < PRE_BATCH; ++k) {
+                const uint32_t i = first + (b0 + k) * PRE_THREADS;
+                if (i < n) {
+                    po[k] = __ldg(a.scene.posop + i);
+                    ca[k] = __ldg(a.scene.cov_a + i);
+                    cb[k] = __ldg(a.scene.cov_b + i);
+                }
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < PRE_BATCH; ++k) {
+                const uint32_t i = first + (b0 + k) * PRE_THREADS;
+                pr[b0 + k] = Projected{ 0u, 0u };
+                if (i < n) {
+                    if (single_entity) {
+                        pr[b0 + k] = project_one(a, i, po[k], ca[k], cb[k], s_vm, s_pm, s_v, s_focal, gx, gy);
+                    } else {
+                        float vm_l[16], pm_l[16];
+                        // an index past the entity table (only possible through tpdcu_upload_gaussians_device, whose indices are
+                        // not validated on the host) must not read outside the matrices
+                        const uint32_t e = min(__ldg(a.scene.entity + i), a.scene.entity_count - 1u);
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) { vm_l[q] = __ldg(a.vm + e * 16 + q); pm_l[q] = __ldg(a.pm + e * 16 + q); }
+                        pr[b0 + k] = project_one(a, i, po[k], ca[k], cb[k], vm_l, pm_l, s_v, s_focal, gx, gy);
+                    }
+                }
+            }
         }
+
+        // ---- depth range of the frame (the depth sort only sorts the bits this range occupies, sort.cu sort_spec) ---------
+        {
+            uint32_t dmin = 0xffffffffu, dmax = 0u;
+#pragma unroll
+            for (uint32_t k = 0; k < PRE_ITEMS; ++k)
+                if (pr[k].count != 0) { dmin = min(dmin, pr[k].depth_bits); dmax = max(dmax, pr[k].depth_bits); }
+            dmin = __reduce_min_sync(0xffffffffu, dmin);
+            dmax = __reduce_max_sync(0xffffffffu, dmax);
+            if (lane == 0 && dmax >= dmin) {  // after the first partitions the range rarely widens: test before the atomic
+                if (dmax > ld_relaxed_u32(&a.ctl->depth_max)) atomicMax(&a.ctl->depth_max, dmax);
+                if (~dmin > ld_relaxed_u32(&a.ctl->inv_depth_min)) atomicMax(&a.ctl->inv_depth_min, ~dmin);
+            }
+        }
+
+        // ---- partition-local exclusive scan of (visible, pairs); group k = Gaussians [k*256, (k+1)*256) of the partition ----
+#pragma unroll
+        for (uint32_t k = 0; k < PRE_ITEMS; ++k) {
+            const uint64_t mine = ((uint64_t)(pr[k].count != 0) << 32) | pr[k].count;
+            uint64_t incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += up;
+            }
+            if (lane == 31) s_warp_tot[par][k][warp] = incl;
+            const uint64_t excl = incl - mine;
+            s_stash[par][k][tid] = make_uint4(pr[k].count, pr[k].depth_bits, (uint32_t)excl, (uint32_t)(excl >> 32));
+        }
+        if (tid == 0) s_part = atomicAdd(&a.ctl->scan_ticket, 1u);   // the next ticket travels during the rest of this turn
+        __syncthreads();
+
+        // ---- warp 0: exclusive scan of the PRE_ITEMS x 8 (group, warp) totals (group-major: the order of the Gaussians), and
+        // the partition's aggregate goes out at once ------------------------------------------------------------------------
+        if (warp == 0) {
+            static_assert(PRE_ITEMS * (PRE_THREADS / 32) == 32, "one lane per (group, warp) total");
+            const uint64_t mine_tot = (&s_warp_tot[par][0][0])[lane];
+            uint64_t incl_tot = mine_tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint64_t up = __shfl_up_sync(0xffffffffu, incl_tot, d);
+                if (lane >= (uint32_t)d) incl_tot += up;
+            }
+            (&s_warp_tot[par][0][0])[lane] = incl_tot - mine_tot;  // exclusive prefix of this (group, warp) inside the partition
+            const uint64_t total = __shfl_sync(0xffffffffu, incl_tot, 31);
+            if (lane == 0) {
+                s_total[par] = total;
+                st_relaxed_u64(a.scan_desc + part, ((uint64_t)(part == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) << 62) | total);
+                // the packed (visible | pairs) scan carries into the visible count once P reaches 2^32: keep an exact 64-bit P
+                // beside it, so that the host can refuse such a frame instead of trusting a wrapped count
+                atomicAdd(&a.ctl->pairs64, (unsigned long long)(uint32_t)total);
+            }
+        }
+
+        // ---- the previous partition of this CTA: every predecessor of it has long published ------------------------------
+        if (prev_part != 0xffffffffu) complete(par ^ 1u);   // (its barrier also orders warp 0's writes above before the reads below)
+        else __syncthreads();
+        prev_part = part;
+        prev_par = par;
+        part = s_part;
+        __syncthreads();   // s_part is rewritten in the next turn, s_base by the next completion
     }
+    if (prev_part != 0xffffffffu) complete(prev_par);
 }
 
 cudaError_t launch_preprocess(const PreprocessLaunch& a, cudaStream_t s) {
     if (a.scene.n == 0) return cudaSuccess;
-    preprocess_kernel<<<(a.scene.n + PRE_PART - 1) / PRE_PART, PRE_THREADS, 0, s>>>(a);
+    // persistent: as many CTAs as stay resident, each drawing partitions by ticket
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
+    }
+    const uint32_t parts = (a.scene.n + PRE_PART - 1) / PRE_PART;
+    preprocess_kernel<<<std::min<uint32_t>(parts, (uint32_t)sm_count * TPDCU_PRE_MINB), PRE_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -404,147 +454,181 @@ constexpr uint32_t EMIT_THREADS = 256;
 constexpr uint32_t EMIT_ITEMS = 4;
 constexpr uint32_t EMIT_PART = EMIT_THREADS * EMIT_ITEMS;
 
-__global__ void __launch_bounds__(EMIT_THREADS, 4) emit_kernel(EmitLaunch a) {
+#ifndef TPDCU_EMIT_MINB
+#define TPDCU_EMIT_MINB 4
+#endif
+// Persistent, like preprocess_kernel: a CTA gathers and scans its next partition, publishes that aggregate, and only then
+// resolves the look-back of its previous partition and emits that partition's pairs — by then every predecessor has published
+// (ncu before: barrier stall 7.9 warps per issue behind the one-warp look-back).
+__global__ void __launch_bounds__(EMIT_THREADS, TPDCU_EMIT_MINB) emit_kernel(EmitLaunch a) {
     __shared__ uint32_t s_part;
     __shared__ uint64_t s_base;
-    __shared__ uint32_t s_off[EMIT_PART];       // exclusive pair offsets inside the partition
-    __shared__ uint32_t s_xy[EMIT_PART];        // rect origin: x0 | y0 << 16
-    __shared__ uint32_t s_w[EMIT_PART];         // rect width | top depth bits << 16 (DepthSplit::extra of them)
-    __shared__ uint32_t s_id[EMIT_PART];        // Gaussian index
+    __shared__ uint32_t s_off[2][EMIT_PART];    // exclusive pair offsets inside the partition     [parity of the CTA's turn]
+    __shared__ uint32_t s_xy[2][EMIT_PART];     // rect origin: x0 | y0 << 16
+    __shared__ uint32_t s_w[2][EMIT_PART];      // rect width | top depth bits << 16 (DepthSplit::extra of them)
+    __shared__ uint32_t s_id[2][EMIT_PART];     // Gaussian index
     __shared__ uint32_t s_warp_tot[EMIT_ITEMS][EMIT_THREADS / 32];
+    __shared__ uint32_t s_total[2];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_part = atomicAdd(&a.ctl->emit_ticket, 1u);
     __syncthreads();
-    const uint32_t part = s_part;
+    uint32_t part = s_part;
     const uint32_t visible = a.depth_plan->n;
-    if ((uint64_t)part * EMIT_PART >= visible) return;
+    const uint32_t num_parts = (visible + EMIT_PART - 1) / EMIT_PART;
     const uint64_t* __restrict__ sorted = a.depth_plan->final_sel ? a.depth_words[1] : a.depth_words[0];
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX;
     const DepthSplit ds = depth_split(a.ctl, a.tile_bits);
+    uint32_t prev_part = 0xffffffffu, prev_par = 0;
 
-    // ---- gather: blocked, so that a thread's EMIT_ITEMS Gaussians are consecutive in depth order -----------------------
-    uint32_t cnt[EMIT_ITEMS];
-#pragma unroll
-    for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
-        const uint32_t slot = k * EMIT_THREADS + tid;           // striped loads (coalesced), partition order = slot order
-        const uint32_t r = part * EMIT_PART + slot;
-        uint32_t id = 0, dtop = 0;
-        uint2 rc = make_uint2(0u, 0u);
-        if (r < visible) {
-            const uint64_t word = __ldg(sorted + r);
-            id = (uint32_t)word;
-            if (ds.extra) dtop = ((uint32_t)(word >> 32) - ds.bias) >> ds.low_bits;
-            rc = __ldg(a.rect + id);
-        }
-        cnt[k] = (rc.y & 0xffffu) * (rc.y >> 16);
-        s_xy[slot] = rc.x;
-        s_w[slot] = (rc.y & 0xffffu) | (dtop << 16);
-        s_id[slot] = id;
-    }
-
-    // ---- partition-local exclusive scan of the tile counts; group k = slots [k*256, (k+1)*256) -------------------------
-    uint32_t incl[EMIT_ITEMS];
-#pragma unroll
-    for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
-        incl[k] = cnt[k];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl[k], d);
-            if (lane >= (uint32_t)d) incl[k] += up;
-        }
-        if (lane == 31) s_warp_tot[k][warp] = incl[k];
-    }
-    __syncthreads();
-    uint32_t total = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
-        uint32_t warp_excl = 0, group_total = 0;
-#pragma unroll
-        for (uint32_t w = 0; w < EMIT_THREADS / 32; ++w) {
-            const uint32_t t = s_warp_tot[k][w];
-            if (w < warp) warp_excl += t;
-            group_total += t;
-        }
-        s_off[k * EMIT_THREADS + tid] = total + warp_excl + incl[k] - cnt[k];
-        total += group_total;
-    }
-
-    // ---- decoupled look-back across partitions (warp 0) ---------------------------------------------
-    if (warp == 0) {
-        uint64_t exclusive = 0;
-        if (part == 0) {
-            if (lane == 0) st_relaxed_u64(a.scan_desc, ((uint64_t)FLAG_PREFIX << 62) | total);
-        } else {
-            if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_AGGREGATE << 62) | total);
-            exclusive = lookback_exclusive(a.scan_desc, part, lane);
-            if (lane == 0) st_relaxed_u64(a.scan_desc + part, ((uint64_t)FLAG_PREFIX << 62) | (exclusive + total));
-        }
-        if (lane == 0) s_base = exclusive;
-    }
-    __syncthreads();
-    const uint32_t base = (uint32_t)s_base;
-
-    // ---- emission: each thread takes groups of four CONSECUTIVE global slots (aligned to 4, so a full group is one 32-byte
-    // store): one binary search finds the Gaussian owning the first slot, the next slots walk forward — the next tile of the
-    // same rectangle (x+1, wrapping to the next row) or the first tile of the next Gaussian. The reference loops serially
-    // per Gaussian; here big and small splats cost the same per pair.
-    const uint32_t slot_end = base + total;
-    for (uint32_t G0 = (base & ~3u) + 4u * tid; G0 < slot_end; G0 += 4u * EMIT_THREADS) {
-        const uint32_t lo = max(G0, base), hi = min(G0 + 4u, slot_end);  // valid global slots of this group: [lo, hi)
-        const uint32_t j = lo - base;
-        uint32_t g = 0;
-#pragma unroll
-        for (uint32_t step = EMIT_PART / 2; step >= 1; step >>= 1)
-            if (s_off[g + step] <= j) g += step;
-        uint32_t wd = s_w[g], xy = s_xy[g], id = s_id[g];
-        uint32_t w = wd & 0xffffu;
-        const uint32_t r = j - s_off[g];
-        const uint32_t ry = r / w;
-        uint32_t rx = r - ry * w;
-        uint32_t row = ((xy >> 16) + ry) * gx + (xy & 0xffffu);  // tile id of the rectangle's column 0 in the current row
-        uint32_t next_off = g + 1 < EMIT_PART ? s_off[g + 1] : 0xffffffffu;
-        uint64_t key[4];
-#pragma unroll
-        for (uint32_t q = 0; q < 4; ++q) {
-            const uint32_t G = G0 + q;
-            if (G >= lo && G < hi) {
-                if (G > lo) {
-                    const uint32_t jq = G - base;
-                    if (jq >= next_off) {  // first tile of the next Gaussian (padding slots of the last partition share their offset)
-                        do {
-                            ++g;
-                            next_off = g + 1 < EMIT_PART ? s_off[g + 1] : 0xffffffffu;
-                        } while (jq >= next_off);
-                        wd = s_w[g]; xy = s_xy[g]; id = s_id[g];
-                        w = wd & 0xffffu;
-                        rx = 0;
-                        row = (xy >> 16) * gx + (xy & 0xffffu);
-                    } else if (++rx == w) {
-                        rx = 0;
-                        row += gx;
-                    }
-                }
-                key[q] = ((uint64_t)(((row + rx) << ds.extra) | (wd >> 16)) << 32) | id;
+    // look-back + emission of partition `prev_part`, whose arrays sit in buffer `par`
+    auto complete = [&](uint32_t par) {
+        const uint32_t total = s_total[par];
+        if (warp == 0) {
+            uint64_t exclusive = 0;
+            if (prev_part != 0) {
+                exclusive = lookback_exclusive(a.scan_desc, prev_part, lane);
+                if (lane == 0) st_relaxed_u64(a.scan_desc + prev_part, ((uint64_t)FLAG_PREFIX << 62) | (exclusive + total));
             }
+            if (lane == 0) s_base = exclusive;
         }
-        if (lo == G0 && hi == G0 + 4u && G0 + 4u <= a.capacity) {
-            stg256(a.keys + G0, key[0], key[1], key[2], key[3]);
-        } else {
+        __syncthreads();
+        const uint32_t base = (uint32_t)s_base;
+        const uint32_t* off = s_off[par];
+        const uint32_t* sw = s_w[par];
+        const uint32_t* sxy = s_xy[par];
+        const uint32_t* sid = s_id[par];
+        // ---- emission: each thread takes groups of four CONSECUTIVE global slots (aligned to 4, so a full group is one
+        // 32-byte store): one binary search finds the Gaussian owning the first slot, the next slots walk forward — the next
+        // tile of the same rectangle (x+1, wrapping to the next row) or the first tile of the next Gaussian. The reference
+        // loops serially per Gaussian; here big and small splats cost the same per pair.
+        const uint32_t slot_end = base + total;
+        for (uint32_t G0 = (base & ~3u) + 4u * tid; G0 < slot_end; G0 += 4u * EMIT_THREADS) {
+            const uint32_t lo = max(G0, base), hi = min(G0 + 4u, slot_end);  // valid global slots of this group: [lo, hi)
+            const uint32_t j = lo - base;
+            uint32_t g = 0;
+#pragma unroll
+            for (uint32_t step = EMIT_PART / 2; step >= 1; step >>= 1)
+                if (off[g + step] <= j) g += step;
+            uint32_t wd = sw[g], xy = sxy[g], id = sid[g];
+            uint32_t w = wd & 0xffffu;
+            const uint32_t r = j - off[g];
+            const uint32_t ry = r / w;
+            uint32_t rx = r - ry * w;
+            uint32_t row = ((xy >> 16) + ry) * gx + (xy & 0xffffu);  // tile id of the rectangle's column 0 in the current row
+            uint32_t next_off = g + 1 < EMIT_PART ? off[g + 1] : 0xffffffffu;
+            uint64_t key[4];
 #pragma unroll
             for (uint32_t q = 0; q < 4; ++q) {
                 const uint32_t G = G0 + q;
-                if (G >= lo && G < hi && G < a.capacity) a.keys[G] = key[q];
+                if (G >= lo && G < hi) {
+                    if (G > lo) {
+                        const uint32_t jq = G - base;
+                        if (jq >= next_off) {  // first tile of the next Gaussian (padding slots of the last partition share their offset)
+                            do {
+                                ++g;
+                                next_off = g + 1 < EMIT_PART ? off[g + 1] : 0xffffffffu;
+                            } while (jq >= next_off);
+                            wd = sw[g]; xy = sxy[g]; id = sid[g];
+                            w = wd & 0xffffu;
+                            rx = 0;
+                            row = (xy >> 16) * gx + (xy & 0xffffu);
+                        } else if (++rx == w) {
+                            rx = 0;
+                            row += gx;
+                        }
+                    }
+                    key[q] = ((uint64_t)(((row + rx) << ds.extra) | (wd >> 16)) << 32) | id;
+                }
+            }
+            if (lo == G0 && hi == G0 + 4u && G0 + 4u <= a.capacity) {
+                stg256(a.keys + G0, key[0], key[1], key[2], key[3]);
+            } else {
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) {
+                    const uint32_t G = G0 + q;
+                    if (G >= lo && G < hi && G < a.capacity) a.keys[G] = key[q];
+                }
             }
         }
+    };
+
+    for (uint32_t turn = 0; part < num_parts; ++turn) {
+        const uint32_t par = turn & 1u;
+        // ---- gather: striped loads (coalesced), partition order = slot order ---------------------------------------------
+        uint32_t cnt[EMIT_ITEMS];
+#pragma unroll
+        for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
+            const uint32_t slot = k * EMIT_THREADS + tid;
+            const uint32_t r = part * EMIT_PART + slot;
+            uint32_t id = 0, dtop = 0;
+            uint2 rc = make_uint2(0u, 0u);
+            if (r < visible) {
+                const uint64_t word = __ldg(sorted + r);
+                id = (uint32_t)word;
+                if (ds.extra) dtop = ((uint32_t)(word >> 32) - ds.bias) >> ds.low_bits;
+                rc = __ldg(a.rect + id);
+            }
+            cnt[k] = (rc.y & 0xffffu) * (rc.y >> 16);
+            s_xy[par][slot] = rc.x;
+            s_w[par][slot] = (rc.y & 0xffffu) | (dtop << 16);
+            s_id[par][slot] = id;
+        }
+
+        // ---- partition-local exclusive scan of the tile counts; group k = slots [k*256, (k+1)*256) -------------------------
+        uint32_t incl[EMIT_ITEMS];
+#pragma unroll
+        for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
+            incl[k] = cnt[k];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl[k], d);
+                if (lane >= (uint32_t)d) incl[k] += up;
+            }
+            if (lane == 31) s_warp_tot[k][warp] = incl[k];
+        }
+        if (tid == 0) s_part = atomicAdd(&a.ctl->emit_ticket, 1u);   // the next ticket travels during the rest of this turn
+        __syncthreads();
+        uint32_t total = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < EMIT_ITEMS; ++k) {
+            uint32_t warp_excl = 0, group_total = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < EMIT_THREADS / 32; ++w) {
+                const uint32_t t = s_warp_tot[k][w];
+                if (w < warp) warp_excl += t;
+                group_total += t;
+            }
+            s_off[par][k * EMIT_THREADS + tid] = total + warp_excl + incl[k] - cnt[k];
+            total += group_total;
+        }
+        if (tid == 0) {   // the partition's aggregate goes out at once
+            s_total[par] = total;
+            st_relaxed_u64(a.scan_desc + part, ((uint64_t)(part == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) << 62) | total);
+        }
+
+        // ---- the previous partition of this CTA: every predecessor of it has long published ------------------------------
+        __syncthreads();   // s_total / s_off of this turn are complete; s_warp_tot may be rewritten
+        if (prev_part != 0xffffffffu) complete(par ^ 1u);
+        prev_part = part;
+        prev_par = par;
+        part = s_part;
+        __syncthreads();   // s_part is rewritten in the next turn, s_base by the next completion, buffer par ^ 1 by the next gather
     }
+    if (prev_part != 0xffffffffu) complete(prev_par);
 }
 
 uint32_t emit_parts(uint32_t n) { return (n + EMIT_PART - 1) / EMIT_PART; }
 
 cudaError_t launch_emit(const EmitLaunch& a, cudaStream_t s) {
     if (a.n == 0) return cudaSuccess;
-    emit_kernel<<<emit_parts(a.n), EMIT_THREADS, 0, s>>>(a);
+    // persistent: as many CTAs as stay resident, each drawing partitions by ticket (the visible count lives on the device)
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
+    }
+    emit_kernel<<<std::min<uint32_t>(emit_parts(a.n), (uint32_t)sm_count * TPDCU_EMIT_MINB), EMIT_THREADS, 0, s>>>(a);
     return cudaGetLastError();
 }
 
