@@ -278,10 +278,18 @@ __device__ __forceinline__ float3 sh_finish(const float (&acc)[3]) {  // + 0.5, 
     return make_float3(fmaxf(__fadd_rn(acc[0], 0.5f), 0.0f), fmaxf(__fadd_rn(acc[1], 0.5f), 0.0f), fmaxf(__fadd_rn(acc[2], 0.5f), 0.0f));
 }
 
+// the same direction with one reciprocal square root (2^-22 relative error: the colour is tolerance-checked, 1/255) instead of
+// an IEEE square root and three IEEE divisions: ~50 instructions less per staged splat of the blend
+__device__ __forceinline__ float3 sh_direction_fast(float px, float py, float pz, const float* cam_pos) {
+    const float dx = px - cam_pos[0], dy = py - cam_pos[1], dz = pz - cam_pos[2];
+    const float inv = rsqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    return make_float3(dx * inv, dy * inv, dz * inv);
+}
 // colour of a Gaussian seen from the camera, its SH row read from global memory
+template <bool FAST_DIRECTION = false>
 __device__ __forceinline__ float3 sh_color(const float4* __restrict__ sh_row, float px, float py, float pz, const float* cam_pos,
                                            int degree) {
-    const float3 d = sh_direction(px, py, pz, cam_pos);
+    const float3 d = FAST_DIRECTION ? sh_direction_fast(px, py, pz, cam_pos) : sh_direction(px, py, pz, cam_pos);
     const ShBasis s = sh_basis(d.x, d.y, d.z, degree);
     const int coefs = sh_coefs(degree);
     float acc[3] = { 0.0f, 0.0f, 0.0f };

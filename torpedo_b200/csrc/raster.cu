@@ -194,6 +194,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     return v;
 }
 
+#ifndef TPDCU_BLEND_FAST_DIRECTION
+#define TPDCU_BLEND_FAST_DIRECTION true
+#endif
 #ifndef TPDCU_BLEND_MINB
 #define TPDCU_BLEND_MINB 7
 #endif
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
 #pragma unroll
                 for (uint32_t q = 0; q < BLEND_WARPS; ++q)
                     if (keep & (2u << q)) sm.list[q][ln[q] + before[q + 1] + __popc(ballot[q + 1] & lanemask_lt())] = (uint16_t)(pos * sizeof(BlendEntry));
-                const float3 c3 = sh_color(a.sh + (size_t)g * SH_PLANES, po.x, po.y, po.z, cam_pos, (int)a.sh_degree);
+                const float3 c3 = sh_color<TPDCU_BLEND_FAST_DIRECTION>(a.sh + (size_t)g * SH_PLANES, po.x, po.y, po.z, cam_pos, (int)a.sh_degree);
                 sm.ent[pos].col = make_float4(c3.x, c3.y, c3.z, 0.0f);
             }
             qn += total[0];

@@ -31,7 +31,7 @@ constexpr uint32_t LOOKBACK_BATCH = TPDCU_LOOKBACK_BATCH;
 #define TPDCU_HIST_CTAS_TILE 2           // histogram CTAs per SM (each adds passes x segments x 256 counters to the global ones)
 #endif
 #ifndef TPDCU_HIST_CTAS_DEPTH
-#define TPDCU_HIST_CTAS_DEPTH 1
+#define TPDCU_HIST_CTAS_DEPTH 2
 #endif
 #ifndef TPDCU_SORT_SWIZZLE
 #define TPDCU_SORT_SWIZZLE 1             // bank swizzle of the per-warp digit counters (hist_slot)
