@@ -18,8 +18,18 @@ constexpr uint32_t SH_PLANES = 12;        // 48 SH floats = 12 float4 per Gaussi
 constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
+#ifndef TPDCU_SORT_TMA
+// 1: the words sorts' next tile arrives in shared memory by cp.async.bulk behind an mbarrier instead of by register loads
+// (sort.cu). Measured on the headline frame: 73 us per tile-sort pass against 69 us, and 0.94 against 0.80 ms/frame with three
+// frames in flight — the second 48 KB buffer per CTA forces 6144-word tiles and leaves the other frames' kernels no shared memory.
+#define TPDCU_SORT_TMA 0
+#endif
 #ifndef TPDCU_SORT_KPT
+#if TPDCU_SORT_TMA
+#define TPDCU_SORT_KPT 24                // 6144-word tiles: two CTAs x (incoming tile + sorted tile) fit the SM's shared memory
+#else
 #define TPDCU_SORT_KPT 32
+#endif
 #endif
 #ifndef TPDCU_SORT_MINB
 #define TPDCU_SORT_MINB 2

@@ -43,7 +43,7 @@ constexpr uint32_t LOOKBACK_BATCH = TPDCU_LOOKBACK_BATCH;
 #define TPDCU_SORT_DRAW_EARLY 1          // 1: the next ticket is drawn before the ranking instead of after it
 #endif
 #ifndef TPDCU_SORT_LOAD_EARLY
-#define TPDCU_SORT_LOAD_EARLY 0          // the next tile's key loads are issued before the look-back (needs DRAW_EARLY)
+#define TPDCU_SORT_LOAD_EARLY TPDCU_SORT_TMA   // the next tile's loads / bulk copy start before the look-back (needs DRAW_EARLY)
 #endif
 #ifndef TPDCU_SORT_RANK_BATCH
 #define TPDCU_SORT_RANK_BATCH 8          // ranking atomics in flight per thread before their keys are scattered
@@ -337,6 +337,11 @@ struct OnesweepSmem {
     uint32_t scan[SORT_BINS / 32];
     uint32_t part;
     uint32_t vals[WITH_VALS ? TILE : 1];
+    // words sorts with TPDCU_SORT_TMA: the CTA's next tile, copied here by cp.async.bulk while the current one is worked on
+    // (+ 2: a tile that starts at an odd element is copied from the element before it, the copy is a whole number of 16 bytes)
+    static constexpr bool TMA = MODE == MODE_WORDS && TPDCU_SORT_TMA;
+    alignas(16) uint64_t raw[TMA ? TILE + 2 : 2];
+    alignas(8) uint64_t bar;
 };
 static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phases");
 
@@ -425,6 +430,39 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     // key loads of a tile, warp-striped: item k of lane l is element warp * 32 * KPT + 32 k + l of the tile; elements at or
     // beyond the segment's end are padding that sorts last
     uint64_t key[SORT_KPT];
+    constexpr bool TMA = Smem::TMA;
+    // TMA form: thread 0 starts the copy of a tile into sm.raw as soon as its ticket is known (no thread waits on a load queue,
+    // no register is held); the CTA picks the keys up from shared memory at the top of the tile's turn. Bulk copies need 16-byte
+    // aligned addresses and sizes: a tile that starts at an odd element is copied from the element before it.
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&sm.bar);
+    auto issue_tile_copy = [&](const TileId& t) {
+        const uint32_t base = t.begin + t.k * SORT_TILE;
+        const uint32_t odd = base & 1u, count = min(SORT_TILE, t.end - base);
+        const uint32_t bytes = (((odd + count) * 8u) + 15u) & ~15u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last read through the generic proxy
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+        const unsigned char* g = reinterpret_cast<const unsigned char*>(src_keys + (base - odd));
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.raw[0]);
+        for (uint32_t o = 0; o < bytes; o += 8192u)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + o), "l"(g + o), "r"(min(8192u, bytes - o)), "r"(bar_s) : "memory");
+    };
+    auto take_keys = [&](const TileId& t, uint32_t parity) {
+        uint32_t ready = 0;
+        while (!ready)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ready) : "r"(bar_s), "r"(parity) : "memory");
+        const uint32_t base = t.begin + t.k * SORT_TILE;
+        const uint32_t count = min(SORT_TILE, t.end - base);
+        const uint32_t at = (base & 1u) + warp * (32u * SORT_KPT) + lane;
+        if (count == SORT_TILE) {
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = sm.raw[at + k * 32u];
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = (at - (base & 1u) + k * 32u) < count ? sm.raw[at + k * 32u] : ~0ull;
+        }
+    };
     auto load_keys = [&](const TileId& t) {
         const uint32_t base = t.begin + t.k * SORT_TILE + warp * (32u * SORT_KPT) + lane;
         if (t.end - (t.begin + t.k * SORT_TILE) >= SORT_TILE) {
@@ -436,11 +474,17 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         }
     };
 
+    if (TMA && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     uint32_t part = sm.part;
     if (part >= total_tiles) return;
     TileId cur = locate(part);
-    load_keys(cur);
+    if (TMA) { if (tid == 0) issue_tile_copy(cur); }
+    else load_keys(cur);
+    uint32_t turn = 0;
     {   // this warp's counters start at zero (a warp only ever counts into its own row)
         uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[warp][0]);
         z[lane] = make_uint4(0, 0, 0, 0);
@@ -457,6 +501,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         const uint32_t warp_base = tile_base + warp * (32u * SORT_KPT) + lane;
         const bool full = n_valid == SORT_TILE;
         if (tid == 0) WS_STAMP(part, 0);
+        if (TMA) take_keys(cur, turn & 1u);
 
         // ---- digits, computed once and packed four to a register; padding (only in a segment's last tile) goes to the top bin
         // What is packed is the digit's COUNTER SLOT, hist_slot(d) = d ^ ((d >> 5) & 3): the per-warp counters are only ever
@@ -564,7 +609,10 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         TileId nxt = cur;
         if (more) {
             nxt = locate(next_part);
-            load_keys(nxt);
+            // TMA: the incoming-tile buffer is free (every thread took its keys before the first barrier of this turn): the
+            // next tile's copy starts now and lands during this tile's look-back and write-out
+            if (TMA) { if (tid == 0) issue_tile_copy(nxt); }
+            else load_keys(nxt);
         }
 #endif
         if (tid == 0) { WS_STAMP(part, 3); WS_STAMP(part, 5); }
@@ -613,7 +661,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         TileId nxt = cur;
         if (more) {
             nxt = locate(next_part);
-            load_keys(nxt);   // this tile's keys sit in shared memory by now: the registers are free
+            if (!TMA) load_keys(nxt);   // this tile's keys sit in shared memory by now: the registers are free
         }
 #endif
 
@@ -656,6 +704,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         // barriers, which no thread passes before it has finished this write-out; sm.part is rewritten after them too
         cur = nxt;
         part = next_part;
+        ++turn;
     }
 }
 

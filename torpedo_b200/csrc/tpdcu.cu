@@ -217,7 +217,7 @@ static int ensure_slot_scene(tpdcu_ctx* c, FrameSlot& f) {
         CK(cudaMalloc(&f.depth_radius, (size_t)c->n * sizeof(float2)));
         CK(cudaMalloc(&f.rect, (size_t)c->n * sizeof(uint2)));
         // whole sort tiles: the onesweep passes prefetch and pad by tile
-        for (int i = 0; i < 2; ++i) CK(cudaMalloc(&f.depth_words[i], align_up(c->n, SORT_TILE) * sizeof(uint64_t)));
+        for (int i = 0; i < 2; ++i) CK(cudaMalloc(&f.depth_words[i], (align_up(c->n, SORT_TILE) + 8) * sizeof(uint64_t)));  // + 8: a tile's bulk copy may read one word past its last
         CK(cudaMalloc(&f.offsets, ((size_t)c->n + 1) * sizeof(uint32_t)));
         CK(cudaMalloc(&f.models, (size_t)c->entity_count * 16 * sizeof(float)));
         CK(cudaMalloc(&f.vm, (size_t)c->entity_count * 16 * sizeof(float)));
@@ -235,7 +235,7 @@ static int ensure_pairs(FrameSlot& f, uint32_t want) {
     if (cap64 > 0xffffffffull - SORT_TILE) return fail(TPDCU_ERR_INVALID, "pair capacity exceeds 2^32");
     free_slot_pairs(f);
     const uint32_t cap = (uint32_t)cap64;
-    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&f.keys[i], (size_t)cap * sizeof(uint64_t)));
+    for (int i = 0; i < 2; ++i) CK(cudaMalloc(&f.keys[i], ((size_t)cap + 8) * sizeof(uint64_t)));  // + 8: a tile's bulk copy may read one word past its last
     f.capacity = cap;
     return TPDCU_OK;
 }
