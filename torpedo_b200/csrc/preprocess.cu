@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(PRE_THREADS, TPDCU_PRE_MINB) preprocess_kernel
     const uint32_t num_parts = (n + PRE_PART - 1) / PRE_PART;
     const uint32_t gx = (a.width + TILE_PX - 1) / TILE_PX, gy = (a.height + TILE_PX - 1) / TILE_PX;
     uint32_t part = s_part;
+    __syncthreads();   // thread 0 rewrites s_part (the next ticket) inside the first turn, before that turn's first barrier
 
     // what a partition leaves behind for its completion, one turn later: per Gaussian its tile count, its depth bits and the
     // exclusive (visible, pairs) prefix inside its warp's group — parked in shared memory, the registers belong to the geometry
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, TPDCU_EMIT_MINB) emit_kernel(Emi
     if (tid == 0) s_part = atomicAdd(&a.ctl->emit_ticket, 1u);
     __syncthreads();
     uint32_t part = s_part;
+    __syncthreads();   // thread 0 rewrites s_part (the next ticket) inside the first turn, before that turn's first barrier
     const uint32_t visible = a.depth_plan->n;
     const uint32_t num_parts = (visible + EMIT_PART - 1) / EMIT_PART;
     const uint64_t* __restrict__ sorted = a.depth_plan->final_sel ? a.depth_words[1] : a.depth_words[0];
