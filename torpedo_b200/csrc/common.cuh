@@ -384,6 +384,7 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
 uint32_t sort_parts(uint32_t capacity, uint32_t kind);
 uint32_t sort_passes_for(uint32_t end_bit);
 cudaError_t init_sort_attributes();
+cudaError_t sort_rank_selftest(uint32_t* mismatches_host);   // lanes whose atomic rank differs from the defined one (must be 0)
 
 struct RasterLaunch {
     const uint64_t* keys[2];              // words tile << 32 | index, sorted

@@ -744,6 +744,45 @@ static cudaError_t set_smem_attr() {
                                 (int)sizeof(OnesweepSmem<MODE>));
 }
 
+// The ranking of onesweep_kernel relies on a property of the hardware that PTX does not promise: a warp's returning
+// shared-memory atomics on one address hand out their values in lane order. This self-test (run once per context by
+// tpdcu_create) ranks 2048 rows of adversarial digit patterns both ways — returning atomics, and match.any + popc, whose
+// result is defined — and counts the rows that differ; a device that fails it is refused rather than sorted unstably.
+__global__ void __launch_bounds__(256) rank_selftest_kernel(uint32_t* mismatches) {
+    __shared__ uint32_t cnt[8][SORT_BINS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t i = lane; i < SORT_BINS; i += 32u) cnt[warp][i] = 0;
+    __syncwarp();
+    uint32_t bad = 0;
+    for (uint32_t row = 0; row < 32u; ++row) {
+        const uint32_t seed = ((blockIdx.x * 8u + warp) * 32u + row) * 32u + lane;
+        uint32_t h = seed * 0x9E3779B1u; h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
+        const uint32_t pattern = (blockIdx.x + row) & 3u;   // random 8-bit | stride 4 | two values | all equal
+        const uint32_t d = pattern == 0 ? (h & 255u) : pattern == 1 ? ((h & 63u) << 2) : pattern == 2 ? (h & 1u) * 77u : (row * 7u) & 255u;
+        const uint32_t before = cnt[warp][d];
+        __syncwarp();
+        uint32_t r;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"((uint32_t)__cvta_generic_to_shared(&cnt[warp][d])) : "memory");
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (r != before + __popc(peers & lanemask_lt())) ++bad;
+        __syncwarp();
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t sort_rank_selftest(uint32_t* mismatches_host) {
+    uint32_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(d, 0, sizeof(uint32_t));
+    if (e == cudaSuccess) {
+        rank_selftest_kernel<<<8, 256>>>(d);
+        e = cudaMemcpy(mismatches_host, d, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    return e;
+}
+
 // opt in to > 48 KB of dynamic shared memory; called once per context, outside any stream capture
 cudaError_t init_sort_attributes() {
     cudaError_t e = set_smem_attr<MODE_PAIRS>();

@@ -638,6 +638,13 @@ int tpdcu_create(int device, tpdcu_ctx** out) {
 #undef CKB
     if (cudaError_t e = init_sort_attributes()) return bail(fail(TPDCU_ERR_CUDA, std::string("init_sort_attributes: ") + cudaGetErrorString(e)));
     if (int r = ensure_status(c)) return bail(r);
+    {   // the onesweep ranking needs lane-ordered returning shared-memory atomics (sort.cu: rank_selftest_kernel)
+        uint32_t mismatches = 0;
+        if (cudaError_t e = sort_rank_selftest(&mismatches)) return bail(fail(TPDCU_ERR_CUDA, std::string("sort_rank_selftest: ") + cudaGetErrorString(e)));
+        if (mismatches != 0)
+            return bail(fail(TPDCU_ERR_CUDA, "this device's shared-memory atomics do not return lane-ordered values (" + std::to_string(mismatches) +
+                                                 " lanes differ): the stable ranking of the radix sort cannot run on it"));
+    }
     *out = c;
     return TPDCU_OK;
 }
