@@ -49,7 +49,7 @@ constexpr uint32_t SORT_WARPS = SORT_THREADS / 32;
 // first pass are equal ranges of positions; segments of pass p > 0 are the runs of 256 / SORT_CHAINS consecutive bins that
 // pass p - 1 wrote (so a key's segment is a function of its previous digit and the histogram kernel can count it).
 #ifndef TPDCU_SORT_CHAINS
-#define TPDCU_SORT_CHAINS 8
+#define TPDCU_SORT_CHAINS 4
 #endif
 constexpr uint32_t SORT_CHAINS = TPDCU_SORT_CHAINS;                    // words sorts; the standalone pair sort runs one chain
 constexpr uint32_t SORT_CHAIN_BINS = SORT_BINS / SORT_CHAINS;          // previous-pass bins per segment

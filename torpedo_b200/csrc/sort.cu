@@ -24,7 +24,7 @@ constexpr uint32_t HIST_THREADS = 512;
 constexpr uint32_t HIST_KPT = 8;
 constexpr uint32_t LOOKBACK_VALUE_MASK = (1u << 30) - 1u;
 #ifndef TPDCU_LOOKBACK_BATCH
-#define TPDCU_LOOKBACK_BATCH 8
+#define TPDCU_LOOKBACK_BATCH 4
 #endif
 constexpr uint32_t LOOKBACK_BATCH = TPDCU_LOOKBACK_BATCH;
 #ifndef TPDCU_HIST_CTAS_TILE
@@ -46,7 +46,10 @@ constexpr uint32_t LOOKBACK_BATCH = TPDCU_LOOKBACK_BATCH;
 #define TPDCU_SORT_LOAD_EARLY TPDCU_SORT_TMA   // the next tile's loads / bulk copy start before the look-back (needs DRAW_EARLY)
 #endif
 #ifndef TPDCU_SORT_RANK_BATCH
-#define TPDCU_SORT_RANK_BATCH 8          // ranking atomics in flight per thread before their keys are scattered
+#define TPDCU_SORT_RANK_BATCH 1          // ranking atomics in flight per thread before their keys are scattered (8: 69 us per pass, 4: 67, 1: 66)
+#endif
+#ifndef TPDCU_SORT_RANK_PIPE
+#define TPDCU_SORT_RANK_PIPE 0           // 1: atomic of key k + 1 issued before the scatter of key k
 #endif
 constexpr uint32_t SORT_RANK_BATCH = TPDCU_SORT_RANK_BATCH;
 #ifndef TPDCU_SORT_MINB_WORDS
@@ -393,9 +396,15 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     // go to different chains, so a chain's consecutive tiles start SORT_CHAINS tickets apart and its look-back is that much
     // shallower. F(k) = sum_c min(tiles_c, k) tickets precede round k; k is the last round that starts at or before the ticket.
     struct TileId { uint32_t chain, k, begin, end, row0; };   // segment, tile of the segment, the segment's range and first row
+    uint32_t min_tiles = 0xffffffffu;
+#pragma unroll
+    for (uint32_t c = 0; c < SORT_CHAINS; ++c) min_tiles = min(min_tiles, seg_tiles[c + 1] - seg_tiles[c]);
     auto locate = [&](uint32_t ticket) {
         TileId t{ 0u, ticket, 0u, 0u, 0u };
-        if (chains > 1) {
+        if (chains > 1 && ticket < SORT_CHAINS * min_tiles) {   // every segment still has tiles: plain round-robin
+            t.chain = ticket % SORT_CHAINS;
+            t.k = ticket / SORT_CHAINS;
+        } else if (chains > 1) {
             auto before_round = [&](uint32_t k) {
                 uint32_t f = 0;
 #pragma unroll
@@ -579,6 +588,20 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         // bit logic; lane order held on all 1.2e8 rows checked). Batches: the atomics of a batch are in flight together, then
         // their keys are scattered.
         uint32_t rank[OUT_PAIRS ? SORT_KPT : 1];
+#if TPDCU_SORT_RANK_PIPE
+        {   // staggered: the atomic of key k + 1 is issued before key k is scattered to the slot its own atomic returned
+            uint32_t r_cur, r_next = 0;
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r_cur) : "r"(hist_row + 4u * digit_at(0)) : "memory");
+#pragma unroll
+            for (uint32_t k = 0; k < SORT_KPT; ++k) {
+                if (k + 1 < SORT_KPT)
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r_next) : "r"(hist_row + 4u * digit_at(k + 1)) : "memory");
+                if (OUT_PAIRS) rank[k] = r_cur;
+                sm.keys[r_cur] = key[k];
+                r_cur = r_next;
+            }
+        }
+#else
 #pragma unroll
         for (uint32_t k0 = 0; k0 < SORT_KPT; k0 += SORT_RANK_BATCH) {
             uint32_t r[SORT_RANK_BATCH];
@@ -591,6 +614,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
                 sm.keys[r[j]] = key[k0 + j];
             }
         }
+#endif
         {   // this warp's counters are free again: zero them for the next tile
             __syncwarp();
             uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[warp][0]);
