@@ -19,7 +19,7 @@ for r in rows:
     if r and r[0] == "Address":
         hdr = r
         continue
-    if k != want or hdr is None or len(r) != len(hdr):
+    if k != want or hdr is None or len(r) != len(hdr) or "L1 Wavefronts Shared" not in hdr:
         continue
     op = r[1].split()
     op = op[1] if op[0].startswith("@") else op[0]
