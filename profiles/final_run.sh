@@ -11,3 +11,4 @@ cp gpurun_out/configs_r1.json gpurun_out/${tag}_configs.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-config5 > gpurun_out/${tag}_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -s 42 -c 14 -o gpurun_out/${tag}_frame python profiles/profile_frame.py 1 > gpurun_out/${tag}_ncu.log 2>&1
 cat gpurun_out/${tag}_pytest_gpu.txt; head -c 400 gpurun_out/${tag}_bench.json; tail -2 gpurun_out/${tag}_ncu.log
+python profiles/sass_evidence.py > gpurun_out/${tag}_sass_opcodes.txt 2>/dev/null
