@@ -502,7 +502,7 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev):
                "views": views, "n_gpus": world, "scaling": "strong", "ms_per_batch": ms, "ms_per_view": ms / views, "views_per_s": views / ms * 1e3,
                "batches_timed": len(times), "gather": f"one NCCL gather per view slot straight into view order, {chunk} slots per asynchronous chunk",
                "frames_repeated": repeated, "views_with_pixels": sum(nonblack),
-               "limiter_at_n8": "8 views per GPU are a ~4 ms job; rank 0 ingests 56 x 8.29 MB = 465 MB over NVLink behind them"}
+               "limiter_at_n8": "8 views per GPU are a ~3.8 ms job plus the fill and drain of the three-frame pipeline; rank 0 ingests 56 x 8.29 MB = 465 MB over NVLink behind them"}
     eng.close()
     return out
 
