@@ -18,18 +18,8 @@ constexpr uint32_t SH_PLANES = 12;        // 48 SH floats = 12 float4 per Gaussi
 constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
-#ifndef TPDCU_SORT_TMA
-// 1: the words sorts' next tile arrives in shared memory by cp.async.bulk behind an mbarrier instead of by register loads
-// (sort.cu). Measured on the headline frame: 73 us per tile-sort pass against 69 us, and 0.94 against 0.80 ms/frame with three
-// frames in flight — the second 48 KB buffer per CTA forces 6144-word tiles and leaves the other frames' kernels no shared memory.
-#define TPDCU_SORT_TMA 0
-#endif
 #ifndef TPDCU_SORT_KPT
-#if TPDCU_SORT_TMA
-#define TPDCU_SORT_KPT 24                // 6144-word tiles: two CTAs x (incoming tile + sorted tile) fit the SM's shared memory
-#else
 #define TPDCU_SORT_KPT 32
-#endif
 #endif
 #ifndef TPDCU_SORT_MINB
 #define TPDCU_SORT_MINB 2
@@ -53,6 +43,13 @@ constexpr uint32_t SORT_WARPS = SORT_THREADS / 32;
 #endif
 constexpr uint32_t SORT_CHAINS = TPDCU_SORT_CHAINS;                    // words sorts; the standalone pair sort runs one chain
 constexpr uint32_t SORT_CHAIN_BINS = SORT_BINS / SORT_CHAINS;          // previous-pass bins per segment
+// Tile sort: every segment's last SORT_HALF_LAST full tiles are cut into half tiles, so that the end of a pass — where 1936
+// tiles over 296 resident CTAs leave the CTAs finishing a whole tile-life apart — is made of half-size work (measured on the
+// headline frame: 0 -> 63.0 us per pass, 9 or 18 -> 61.7-62.5, 37 -> 63.5; the depth sort, two tiles per CTA, loses with any).
+#ifndef TPDCU_SORT_HALF_LAST
+#define TPDCU_SORT_HALF_LAST (296 / 4 / TPDCU_SORT_CHAINS)
+#endif
+constexpr uint32_t SORT_HALF_LAST = TPDCU_SORT_HALF_LAST;
 constexpr uint32_t SORT_WORD_PASSES = 4;                               // words sorts order at most 32 key bits
 constexpr uint32_t SORT_CHAIN_ROWS = SORT_WORD_PASSES * SORT_CHAINS > SORT_MAX_PASSES ? SORT_WORD_PASSES * SORT_CHAINS : SORT_MAX_PASSES;
 static_assert((SORT_CHAINS & (SORT_CHAINS - 1)) == 0 && SORT_CHAINS <= 32, "SORT_CHAINS is a power of two");
@@ -112,6 +109,7 @@ struct SortPlan {
     uint32_t skip[SORT_MAX_PASSES];       // pass is an identity permutation (single occupied bin)
     uint32_t src_sel[SORT_MAX_PASSES];    // ping-pong buffer the pass reads from
     uint32_t chains;                      // look-back chains per pass: SORT_CHAINS (words) or 1 (pairs)
+    uint32_t half_last;                   // per segment, the last this many full tiles' worth of elements is cut into half tiles
     uint32_t seg_start[SORT_MAX_PASSES][SORT_CHAINS + 1];   // first input position of every segment of the pass (+ n)
     uint32_t seg_tiles[SORT_MAX_PASSES][SORT_CHAINS + 1];   // tiles of the segments before c: descriptor row of its tile 0 (+ total)
 };

@@ -39,19 +39,6 @@ constexpr uint32_t LOOKBACK_BATCH = TPDCU_LOOKBACK_BATCH;
 #ifndef TPDCU_SORT_GRID_FACTOR
 #define TPDCU_SORT_GRID_FACTOR 1         // CTAs launched per resident slot of the persistent pass kernel
 #endif
-#ifndef TPDCU_SORT_DRAW_EARLY
-#define TPDCU_SORT_DRAW_EARLY 1          // 1: the next ticket is drawn before the ranking instead of after it
-#endif
-#ifndef TPDCU_SORT_LOAD_EARLY
-#define TPDCU_SORT_LOAD_EARLY TPDCU_SORT_TMA   // the next tile's loads / bulk copy start before the look-back (needs DRAW_EARLY)
-#endif
-#ifndef TPDCU_SORT_RANK_BATCH
-#define TPDCU_SORT_RANK_BATCH 1          // ranking atomics in flight per thread before their keys are scattered (8: 69 us per pass, 4: 67, 1: 66)
-#endif
-#ifndef TPDCU_SORT_RANK_PIPE
-#define TPDCU_SORT_RANK_PIPE 0           // 1: atomic of key k + 1 issued before the scatter of key k
-#endif
-constexpr uint32_t SORT_RANK_BATCH = TPDCU_SORT_RANK_BATCH;
 #ifndef TPDCU_SORT_MINB_WORDS
 #define TPDCU_SORT_MINB_WORDS 2
 #endif
@@ -110,6 +97,19 @@ __host__ __device__ __forceinline__ uint32_t passes_needed(uint32_t total_bits) 
 
 __device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, SortPlan* plan, uint32_t kind, uint32_t n_host,
                                           uint32_t capacity, uint32_t end_bit, uint32_t tile_bits);
+
+// Tiles of a segment of `len` elements: full tiles of `tile` elements, except that the segment's last `half_last` full tiles'
+// worth of elements is cut into half tiles (words sorts: the last tickets of a pass go to half tiles, so that the resident CTAs
+// finish half a tile-life apart instead of a whole one). Shared by the plan and the pass kernel.
+struct SegTiles { uint32_t full, total; };
+__host__ __device__ __forceinline__ SegTiles seg_tile_counts(uint32_t len, uint32_t tile, uint32_t half_last) {
+    const uint32_t whole = (len + tile - 1) / tile;
+    SegTiles t;
+    t.full = whole > half_last ? whole - half_last : 0u;
+    const uint32_t rest = len - min(len, t.full * tile);
+    t.total = t.full + (rest + tile / 2 - 1) / (tile / 2);
+    return t;
+}
 
 __host__ __device__ __forceinline__ uint32_t chains_of(uint32_t kind) { return kind == SORT_KIND_PAIRS ? 1u : SORT_CHAINS; }
 __host__ __device__ __forceinline__ uint32_t tile_of(uint32_t kind) { return kind == SORT_KIND_PAIRS ? SORT_TILE_PAIRS : SORT_TILE_WORDS; }
@@ -285,6 +285,8 @@ __device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, S
         // segments of every pass's input and the descriptor rows of their tiles. A pass that follows an identity pass finds
         // every key in one previous bin: one segment covers [0, n) and the others are empty, which is what its keys' counts say.
         plan->chains = chains;
+        const uint32_t half_last = kind == SORT_KIND_TILE ? SORT_HALF_LAST : 0u;   // the depth sort has two tiles per CTA: more, smaller tiles cost it more than its tail
+        plan->half_last = half_last;
         const uint32_t tile = tile_of(kind), seg0 = first_pass_segment(n, kind);
         for (uint32_t p = 0; p < num_passes; ++p) {
             uint32_t rows = 0;
@@ -295,7 +297,7 @@ __device__ __forceinline__ void make_plan(const FrameCtl* frame, SortCtl* ctl, S
             }
             for (uint32_t ch = 0; ch <= SORT_CHAINS; ++ch) {
                 plan->seg_tiles[p][ch] = rows;
-                if (ch < SORT_CHAINS) rows += (plan->seg_start[p][ch + 1] - plan->seg_start[p][ch] + tile - 1) / tile;
+                if (ch < SORT_CHAINS) rows += seg_tile_counts(plan->seg_start[p][ch + 1] - plan->seg_start[p][ch], tile, half_last).total;
             }
         }
     }
@@ -340,23 +342,18 @@ struct OnesweepSmem {
     uint32_t scan[SORT_BINS / 32];
     uint32_t part;
     uint32_t vals[WITH_VALS ? TILE : 1];
-    // words sorts with TPDCU_SORT_TMA: the CTA's next tile, copied here by cp.async.bulk while the current one is worked on
-    // (+ 2: a tile that starts at an odd element is copied from the element before it, the copy is a whole number of 16 bytes)
-    static constexpr bool TMA = MODE == MODE_WORDS && TPDCU_SORT_TMA;
-    alignas(16) uint64_t raw[TMA ? TILE + 2 : 2];
-    alignas(8) uint64_t bar;
 };
 static_assert(SORT_THREADS == SORT_BINS, "one thread per bin in the per-bin phases");
 
-// A resident CTA works through tiles of TILE elements, one ticket at a time. Per tile (block barriers in between):
+// A resident CTA works through tiles of TILE (or TILE / 2) elements, one ticket at a time. Per tile (block barriers in between):
 //   digits + counting atomics (keys already in registers) | per bin: prefix over the warps, publish the aggregate, scan the
-//   bins | ranking atomics + scatter to smem | draw the NEXT ticket, issue the next tile's key loads | look-back per bin |
+//   bins; draw the NEXT ticket | ranking atomics + scatter to smem | look-back per bin | the next tile's key loads are issued |
 //   coalesced write-out (+ value scatter / write-out) | next tile.
 // Between a CTA's end and its successor's first load lie a block launch, a ticket round trip and the plan loads — 2 us of a
 // 10 us tile life with one tile per CTA (per-tile trace, profiles/micro/ws_trace.cu); the loop pays them once per CTA, and
-// the next tile's keys travel while this tile's look-back and write-out run. The next ticket is drawn AFTER this tile's
-// ranking, i.e. at a fixed phase of every CTA's cycle: tickets are handed out in the order the tiles will really be
-// started, which keeps the look-back from waiting on a tile whose CTA is still busy with the previous one.
+// the next tile's keys travel while this tile's write-out runs. The next ticket is drawn at a fixed phase of every CTA's
+// cycle: tickets are handed out in the order the tiles will really be started, which keeps the look-back from waiting on a
+// tile whose CTA is still busy with the previous one.
 template <int MODE>
 __global__ void __launch_bounds__(SORT_THREADS, MODE == MODE_WORDS ? TPDCU_SORT_MINB_WORDS : TPDCU_SORT_MINB)
 onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* vals1, SortCtl* ctl,
@@ -364,7 +361,9 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     constexpr bool IN_PAIRS = MODE == MODE_PAIRS, OUT_PAIRS = MODE == MODE_PAIRS, WORDS = MODE == MODE_WORDS;
     using Smem = OnesweepSmem<MODE>;
     constexpr uint32_t SORT_KPT = MODE == MODE_PAIRS ? SORT_KPT_PAIRS : SORT_KPT_WORDS;  // shadows nothing: per-mode tile shape
+    constexpr uint32_t HALF_KPT = SORT_KPT / 2;
     constexpr uint32_t SORT_TILE = Smem::TILE;
+    static_assert(SORT_KPT % 8 == 0, "half tiles pack whole digit registers");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
@@ -378,7 +377,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         seg_start[c] = plan->seg_start[pass][c];
         seg_tiles[c] = plan->seg_tiles[pass][c];
     }
-    const uint32_t chains = plan->chains;
+    const uint32_t chains = plan->chains, half_last = plan->half_last;
     const uint32_t total_tiles = seg_tiles[SORT_CHAINS];
     const uint32_t src = plan->src_sel[pass];
     const uint64_t* __restrict__ src_keys = src ? keys1 : keys0;
@@ -395,12 +394,13 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     // Ticket -> (segment c, tile k of that segment), round-robin over the segments that still have tiles: consecutive tickets
     // go to different chains, so a chain's consecutive tiles start SORT_CHAINS tickets apart and its look-back is that much
     // shallower. F(k) = sum_c min(tiles_c, k) tickets precede round k; k is the last round that starts at or before the ticket.
-    struct TileId { uint32_t chain, k, begin, end, row0; };   // segment, tile of the segment, the segment's range and first row
+    // A tile is `rows` 32-key rows per thread: SORT_KPT, or half of that for a segment's last tiles (seg_tile_counts).
+    struct TileId { uint32_t chain, k, row0, base, end, rows; };   // segment, tile of it, its first descriptor row, elements [base, end) at most
     uint32_t min_tiles = 0xffffffffu;
 #pragma unroll
     for (uint32_t c = 0; c < SORT_CHAINS; ++c) min_tiles = min(min_tiles, seg_tiles[c + 1] - seg_tiles[c]);
     auto locate = [&](uint32_t ticket) {
-        TileId t{ 0u, ticket, 0u, 0u, 0u };
+        TileId t{ 0u, ticket, 0u, 0u, 0u, SORT_KPT };
         if (chains > 1 && ticket < SORT_CHAINS * min_tiles) {   // every segment still has tiles: plain round-robin
             t.chain = ticket % SORT_CHAINS;
             t.k = ticket / SORT_CHAINS;
@@ -431,69 +431,42 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
                 }
             }
         }
+        uint32_t begin = 0;
 #pragma unroll
         for (uint32_t c = 0; c < SORT_CHAINS; ++c)
-            if (c == t.chain) { t.begin = seg_start[c]; t.end = seg_start[c + 1]; t.row0 = seg_tiles[c]; }
+            if (c == t.chain) { begin = seg_start[c]; t.end = seg_start[c + 1]; t.row0 = seg_tiles[c]; }
+        const uint32_t full = seg_tile_counts(t.end - begin, SORT_TILE, half_last).full;
+        if (t.k < full) {
+            t.base = begin + t.k * SORT_TILE;
+        } else {
+            t.base = begin + full * SORT_TILE + (t.k - full) * (SORT_TILE / 2);
+            t.rows = HALF_KPT;
+        }
         return t;
     };
-    // key loads of a tile, warp-striped: item k of lane l is element warp * 32 * KPT + 32 k + l of the tile; elements at or
+    // key loads of a tile, warp-striped: item k of lane l is element warp * 32 * rows + 32 k + l of the tile; elements at or
     // beyond the segment's end are padding that sorts last
     uint64_t key[SORT_KPT];
-    constexpr bool TMA = Smem::TMA;
-    // TMA form: thread 0 starts the copy of a tile into sm.raw as soon as its ticket is known (no thread waits on a load queue,
-    // no register is held); the CTA picks the keys up from shared memory at the top of the tile's turn. Bulk copies need 16-byte
-    // aligned addresses and sizes: a tile that starts at an odd element is copied from the element before it.
-    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&sm.bar);
-    auto issue_tile_copy = [&](const TileId& t) {
-        const uint32_t base = t.begin + t.k * SORT_TILE;
-        const uint32_t odd = base & 1u, count = min(SORT_TILE, t.end - base);
-        const uint32_t bytes = (((odd + count) * 8u) + 15u) & ~15u;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last read through the generic proxy
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
-        const unsigned char* g = reinterpret_cast<const unsigned char*>(src_keys + (base - odd));
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.raw[0]);
-        for (uint32_t o = 0; o < bytes; o += 8192u)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst + o), "l"(g + o), "r"(min(8192u, bytes - o)), "r"(bar_s) : "memory");
-    };
-    auto take_keys = [&](const TileId& t, uint32_t parity) {
-        uint32_t ready = 0;
-        while (!ready)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                         : "=r"(ready) : "r"(bar_s), "r"(parity) : "memory");
-        const uint32_t base = t.begin + t.k * SORT_TILE;
-        const uint32_t count = min(SORT_TILE, t.end - base);
-        const uint32_t at = (base & 1u) + warp * (32u * SORT_KPT) + lane;
-        if (count == SORT_TILE) {
-#pragma unroll
-            for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = sm.raw[at + k * 32u];
-        } else {
-#pragma unroll
-            for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = (at - (base & 1u) + k * 32u) < count ? sm.raw[at + k * 32u] : ~0ull;
-        }
-    };
     auto load_keys = [&](const TileId& t) {
-        const uint32_t base = t.begin + t.k * SORT_TILE + warp * (32u * SORT_KPT) + lane;
-        if (t.end - (t.begin + t.k * SORT_TILE) >= SORT_TILE) {
+        const uint32_t at = t.base + warp * (32u * t.rows) + lane;
+        if (t.end - t.base >= t.rows * SORT_THREADS) {
 #pragma unroll
-            for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = src_keys[base + k * 32u];
+            for (uint32_t k = 0; k < HALF_KPT; ++k) key[k] = src_keys[at + k * 32u];
+            if (t.rows > HALF_KPT) {
+#pragma unroll
+                for (uint32_t k = HALF_KPT; k < SORT_KPT; ++k) key[k] = src_keys[at + k * 32u];
+            }
         } else {
 #pragma unroll
-            for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = (base + k * 32u) < t.end ? src_keys[base + k * 32u] : ~0ull;
+            for (uint32_t k = 0; k < SORT_KPT; ++k) key[k] = (k < t.rows && (at + k * 32u) < t.end) ? src_keys[at + k * 32u] : ~0ull;
         }
     };
 
-    if (TMA && tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
     uint32_t part = sm.part;
     if (part >= total_tiles) return;
     TileId cur = locate(part);
-    if (TMA) { if (tid == 0) issue_tile_copy(cur); }
-    else load_keys(cur);
-    uint32_t turn = 0;
+    load_keys(cur);
     {   // this warp's counters start at zero (a warp only ever counts into its own row)
         uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[warp][0]);
         z[lane] = make_uint4(0, 0, 0, 0);
@@ -502,15 +475,17 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     }
 
     for (;;) {
-        const uint32_t tile_base = cur.begin + cur.k * SORT_TILE;
+        const uint32_t rows = cur.rows;                   // 32-key rows per thread in this tile (uniform)
+        const bool whole = rows > HALF_KPT;               // a full-size tile: the second half of every per-key loop runs
+        const uint32_t tile_keys = rows * SORT_THREADS;
+        const uint32_t tile_base = cur.base;
         const uint32_t n = cur.end;                       // elements at or beyond the segment's end are padding
-        const uint32_t n_valid = min(SORT_TILE, cur.end - tile_base);
+        const uint32_t n_valid = min(tile_keys, cur.end - tile_base);
         const uint32_t row = cur.row0 + cur.k;            // this tile's descriptor row; its chain's rows are row0 .. row
         const uint32_t chain = cur.chain, k_tile = cur.k, row0 = cur.row0;
-        const uint32_t warp_base = tile_base + warp * (32u * SORT_KPT) + lane;
-        const bool full = n_valid == SORT_TILE;
+        const uint32_t warp_base = tile_base + warp * (32u * rows) + lane;
+        const bool full = n_valid == tile_keys;
         if (tid == 0) WS_STAMP(part, 0);
-        if (TMA) take_keys(cur, turn & 1u);
 
         // ---- digits, computed once and packed four to a register; padding (only in a segment's last tile) goes to the top bin
         // What is packed is the digit's COUNTER SLOT, hist_slot(d) = d ^ ((d >> 5) & 3): the per-warp counters are only ever
@@ -519,8 +494,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         // wavefronts per ranking atomic, 5.6 per counting atomic). XOR-ing bits 5-6 into bits 0-1 spreads a stride-4 run over
         // all banks and still maps 32 consecutive bins (a warp of the thread == bin phases) onto 32 distinct banks.
         uint32_t dpack[SORT_KPT / 4];
-#pragma unroll
-        for (uint32_t q = 0; q < SORT_KPT / 4; ++q) {
+        auto pack_digits = [&](uint32_t q) {
             uint32_t w = 0;
 #pragma unroll
             for (uint32_t r = 0; r < 4; ++r) {
@@ -529,14 +503,24 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
                 w |= hist_slot(valid ? digit_in(key[k]) : mask) << (8u * r);
             }
             dpack[q] = w;
+        };
+#pragma unroll
+        for (uint32_t q = 0; q < HALF_KPT / 4; ++q) pack_digits(q);
+        if (whole) {
+#pragma unroll
+            for (uint32_t q = HALF_KPT / 4; q < SORT_KPT / 4; ++q) pack_digits(q);
         }
         auto digit_at = [&](uint32_t k) { return (dpack[k >> 2] >> (8u * (k & 3u))) & 0xffu; };
 
         // ---- early counts: per-warp digit histograms ----------------------------------------------------
 #pragma unroll
-        for (uint32_t k = 0; k < SORT_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_at(k)], 1u);
+        for (uint32_t k = 0; k < HALF_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_at(k)], 1u);
+        if (whole) {
+#pragma unroll
+            for (uint32_t k = HALF_KPT; k < SORT_KPT; ++k) atomicAdd(&sm.warp_hist[warp][digit_at(k)], 1u);
+        }
 
-        // values (pair input): issue the loads now, their latency hides behind the per-bin phases
+        // values (pair input; always whole tiles): issue the loads now, their latency hides behind the per-bin phases
         uint32_t val[IN_PAIRS ? SORT_KPT : 1];
         if (IN_PAIRS) {
             if (full) {
@@ -558,7 +542,7 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
             sm.warp_hist[w][my_slot] = bin_count;
             bin_count += c;
         }
-        const uint32_t bin_count_valid = (tid == mask) ? bin_count - (SORT_TILE - n_valid) : bin_count;  // padding lives in the top bin
+        const uint32_t bin_count_valid = (tid == mask) ? bin_count - (tile_keys - n_valid) : bin_count;  // padding lives in the top bin
         if (tid == 0) { WS_STAMP(part, 1); WS_STAMP(part, 2); }
         st_relaxed_u32(lb + tid, ((k_tile == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) << 30) | bin_count_valid);
         uint32_t incl = bin_count;
@@ -576,69 +560,34 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
 #pragma unroll
         for (uint32_t w = 0; w < SORT_WARPS; ++w) sm.warp_hist[w][my_slot] += bin_base;
         uint32_t next_ticket = 0;
-#if TPDCU_SORT_DRAW_EARLY
         if (tid == 0) next_ticket = atomicAdd(&ctl->ticket[pass], 1u);   // the next ticket travels while this tile is ranked
-#endif
         __syncthreads();
 
         // ---- stable ranking: one returning shared-memory atomic per key; elements go straight to smem ---------------------
-        // ATOMS.POPC.INC with a destination register hands every lane the counter's value plus the number of LOWER lanes of
-        // the same instruction that hit the same counter, i.e. the stable rank, and a warp's atomics execute in program order,
-        // so rows stay ordered too (profiles/micro/atoms_rank.cu: 7-20 cycles per row and SM against 30-42 for eight ballots +
-        // bit logic; lane order held on all 1.2e8 rows checked). Batches: the atomics of a batch are in flight together, then
-        // their keys are scattered.
+        // ATOMS with a destination register hands every lane the counter's value plus the number of LOWER lanes of the same
+        // instruction that hit the same counter, i.e. the stable rank, and a warp's atomics execute in program order, so rows
+        // stay ordered too (profiles/micro/atoms_rank.cu: 7-20 cycles per row and SM against 30-42 for eight ballots + bit logic;
+        // lane order held on all 1.2e8 rows checked, and tpdcu_create re-checks it on the device: rank_selftest_kernel). Every
+        // atomic is followed at once by its key's scatter (batches of 8 in flight: 69 us per tile-sort pass, 4: 67, 1: 66).
         uint32_t rank[OUT_PAIRS ? SORT_KPT : 1];
-#if TPDCU_SORT_RANK_PIPE
-        {   // staggered: the atomic of key k + 1 is issued before key k is scattered to the slot its own atomic returned
-            uint32_t r_cur, r_next = 0;
-            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r_cur) : "r"(hist_row + 4u * digit_at(0)) : "memory");
+        auto rank_one = [&](uint32_t k) {
+            uint32_t r;
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r) : "r"(hist_row + 4u * digit_at(k)) : "memory");
+            if (OUT_PAIRS) rank[k] = r;
+            sm.keys[r] = key[k];
+        };
 #pragma unroll
-            for (uint32_t k = 0; k < SORT_KPT; ++k) {
-                if (k + 1 < SORT_KPT)
-                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r_next) : "r"(hist_row + 4u * digit_at(k + 1)) : "memory");
-                if (OUT_PAIRS) rank[k] = r_cur;
-                sm.keys[r_cur] = key[k];
-                r_cur = r_next;
-            }
+        for (uint32_t k = 0; k < HALF_KPT; ++k) rank_one(k);
+        if (whole) {
+#pragma unroll
+            for (uint32_t k = HALF_KPT; k < SORT_KPT; ++k) rank_one(k);
         }
-#else
-#pragma unroll
-        for (uint32_t k0 = 0; k0 < SORT_KPT; k0 += SORT_RANK_BATCH) {
-            uint32_t r[SORT_RANK_BATCH];
-#pragma unroll
-            for (uint32_t j = 0; j < SORT_RANK_BATCH; ++j)
-                asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(r[j]) : "r"(hist_row + 4u * digit_at(k0 + j)) : "memory");
-#pragma unroll
-            for (uint32_t j = 0; j < SORT_RANK_BATCH; ++j) {
-                if (OUT_PAIRS) rank[k0 + j] = r[j];
-                sm.keys[r[j]] = key[k0 + j];
-            }
-        }
-#endif
         {   // this warp's counters are free again: zero them for the next tile
             __syncwarp();
             uint4* z = reinterpret_cast<uint4*>(&sm.warp_hist[warp][0]);
             z[lane] = make_uint4(0, 0, 0, 0);
             z[lane + 32] = make_uint4(0, 0, 0, 0);
         }
-#if !TPDCU_SORT_DRAW_EARLY
-        if (tid == 0) next_ticket = atomicAdd(&ctl->ticket[pass], 1u);   // travels while this tile's look-back runs
-#endif
-#if TPDCU_SORT_DRAW_EARLY && TPDCU_SORT_LOAD_EARLY
-        // ---- the next tile: its ticket arrived during the ranking; its keys travel during the look-back and the write-out ------
-        if (tid == 0) sm.part = next_ticket;
-        __syncthreads();   // also: every key of this tile is in shared memory, the key registers are free
-        const uint32_t next_part = sm.part;
-        const bool more = next_part < total_tiles;
-        TileId nxt = cur;
-        if (more) {
-            nxt = locate(next_part);
-            // TMA: the incoming-tile buffer is free (every thread took its keys before the first barrier of this turn): the
-            // next tile's copy starts now and lands during this tile's look-back and write-out
-            if (TMA) { if (tid == 0) issue_tile_copy(nxt); }
-            else load_keys(nxt);
-        }
-#endif
         if (tid == 0) { WS_STAMP(part, 3); WS_STAMP(part, 5); }
 
         // ---- decoupled look-back, one thread per bin -----------------------------------------------------
@@ -673,9 +622,6 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         // bin's output run + keys of the earlier segments in that bin + keys of this segment's earlier tiles - tile-local offset
         sm.global_base[tid] = ctl->hist[pass][tid] + ctl->chain_hist[pass * chains + chain][tid] + excl - bin_base;
         if (tid == 0) { WS_STAMP(part, 4); WS_STAMP(part, 6); WS_NOTE(part, 8, (unsigned long long)trace_rows); WS_NOTE(part, 9, 0ull); WS_NOTE(part, 10, (unsigned long long)chain); }
-#if TPDCU_SORT_DRAW_EARLY && TPDCU_SORT_LOAD_EARLY
-        __syncthreads();
-#else
         if (tid == 0) sm.part = next_ticket;
         __syncthreads();
 
@@ -685,32 +631,30 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         TileId nxt = cur;
         if (more) {
             nxt = locate(next_part);
-            if (!TMA) load_keys(nxt);   // this tile's keys sit in shared memory by now: the registers are free
+            load_keys(nxt);   // this tile's keys sit in shared memory by now: the registers are free
         }
-#endif
 
         // ---- write-out: position i of the locally sorted tile goes to global_base[digit] + i (contiguous per bin) ---------
         uint32_t pos[OUT_PAIRS ? SORT_KPT : 1];
-        if (full) {  // every tile but a segment's last: no per-key bounds branch
-#pragma unroll
-            for (uint32_t k = 0; k < SORT_KPT; ++k) {
-                const uint32_t i = tid + k * SORT_THREADS;
+        auto write_one = [&](uint32_t k, bool guarded) {
+            const uint32_t i = tid + k * SORT_THREADS;
+            if (!guarded || i < n_valid) {
                 const uint64_t kk = sm.keys[i];
                 const uint32_t p = sm.global_base[digit_out(kk)] + i;
                 if (OUT_PAIRS) pos[k] = p;
                 dst_keys[p] = kk;
             }
+        };
+        if (full) {  // every tile but a segment's last: no per-key bounds branch
+#pragma unroll
+            for (uint32_t k = 0; k < HALF_KPT; ++k) write_one(k, false);
+            if (whole) {
+#pragma unroll
+                for (uint32_t k = HALF_KPT; k < SORT_KPT; ++k) write_one(k, false);
+            }
         } else {
 #pragma unroll
-            for (uint32_t k = 0; k < SORT_KPT; ++k) {
-                const uint32_t i = tid + k * SORT_THREADS;
-                if (i < n_valid) {
-                    const uint64_t kk = sm.keys[i];
-                    const uint32_t p = sm.global_base[digit_out(kk)] + i;
-                    if (OUT_PAIRS) pos[k] = p;
-                    dst_keys[p] = kk;
-                }
-            }
+            for (uint32_t k = 0; k < SORT_KPT; ++k) write_one(k, true);
         }
         if (tid == 0) WS_STAMP(part, 7);
         if (OUT_PAIRS) {
@@ -728,7 +672,6 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
         // barriers, which no thread passes before it has finished this write-out; sm.part is rewritten after them too
         cur = nxt;
         part = next_part;
-        ++turn;
     }
 }
 
@@ -757,8 +700,9 @@ __global__ void sort_copy_result_kernel(const uint64_t* keys1, const uint32_t* v
 
 // upper bound of the tiles (= look-back descriptor rows, = CTAs) of a pass: every segment may end in a partial tile
 uint32_t sort_parts(uint32_t capacity, uint32_t kind) {
-    const uint32_t tile = tile_of(kind);
-    return (capacity + tile - 1) / tile + chains_of(kind);
+    const uint32_t tile = tile_of(kind), chains = chains_of(kind);
+    // + per segment: a partial last tile, and SORT_HALF_LAST full tiles turned into twice as many half tiles (+ 1 for rounding)
+    return (capacity + tile - 1) / tile + chains * (kind == SORT_KIND_PAIRS ? 1u : SORT_HALF_LAST + 2u);
 }
 uint32_t sort_passes_for(uint32_t end_bit) { return passes_needed(end_bit); }
 
