@@ -180,7 +180,13 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
                 const uint32_t c = p == 0 ? (chains > 1 ? c_first + (j >= c_change ? 1u : 0u) : 0u) : ((uint32_t)(k[j] >> seg_shift) & seg_mask);
                 return row_base + (c << SORT_RADIX_BITS) + hist_slot(d);   // bank swizzle: the tile sort's low digits sit at stride 4
             };
-            if (valid == HIST_KPT) {
+            if (valid == HIST_KPT && p == 0 && kind == SORT_KIND_TILE) {
+                // the pairs' low tile bits change with every element (a Gaussian's tiles are emitted row by row): no runs to
+                // encode, one counting atomic per element is cheaper than looking for them
+#pragma unroll
+                for (uint32_t j = 0; j < HIST_KPT; ++j)
+                    asm volatile("red.shared.add.u32 [%0], 1;" : : "r"(h_s + 4u * slot(j)) : "memory");
+            } else if (valid == HIST_KPT) {
                 // run-length encode the eight slots; a run is flushed by ONE predicated shared-memory reduction (no branch:
                 // the compiler's divergent-branch form of `if (changed) atomicAdd` cost 4 of 22 instructions per key and pass)
                 uint32_t run_slot = slot(0), run = 1;
