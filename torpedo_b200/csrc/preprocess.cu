@@ -455,6 +455,9 @@ constexpr uint32_t EMIT_THREADS = 256;
 constexpr uint32_t EMIT_ITEMS = 4;
 constexpr uint32_t EMIT_PART = EMIT_THREADS * EMIT_ITEMS;
 
+#ifndef TPDCU_EMIT_GROUP
+#define TPDCU_EMIT_GROUP 4
+#endif
 #ifndef TPDCU_EMIT_MINB
 #define TPDCU_EMIT_MINB 4
 #endif
@@ -505,8 +508,9 @@ __global__ void __launch_bounds__(EMIT_THREADS, TPDCU_EMIT_MINB) emit_kernel(Emi
         // tile of the same rectangle (x+1, wrapping to the next row) or the first tile of the next Gaussian. The reference
         // loops serially per Gaussian; here big and small splats cost the same per pair.
         const uint32_t slot_end = base + total;
-        for (uint32_t G0 = (base & ~3u) + 4u * tid; G0 < slot_end; G0 += 4u * EMIT_THREADS) {
-            const uint32_t lo = max(G0, base), hi = min(G0 + 4u, slot_end);  // valid global slots of this group: [lo, hi)
+        constexpr uint32_t GROUP = TPDCU_EMIT_GROUP;   // consecutive slots per thread and search: whole 32-byte stores
+        for (uint32_t G0 = (base & ~(GROUP - 1u)) + GROUP * tid; G0 < slot_end; G0 += GROUP * EMIT_THREADS) {
+            const uint32_t lo = max(G0, base), hi = min(G0 + GROUP, slot_end);  // valid global slots of this group: [lo, hi)
             const uint32_t j = lo - base;
             uint32_t g = 0;
 #pragma unroll
@@ -519,9 +523,9 @@ __global__ void __launch_bounds__(EMIT_THREADS, TPDCU_EMIT_MINB) emit_kernel(Emi
             uint32_t rx = r - ry * w;
             uint32_t row = ((xy >> 16) + ry) * gx + (xy & 0xffffu);  // tile id of the rectangle's column 0 in the current row
             uint32_t next_off = g + 1 < EMIT_PART ? off[g + 1] : 0xffffffffu;
-            uint64_t key[4];
+            uint64_t key[GROUP];
 #pragma unroll
-            for (uint32_t q = 0; q < 4; ++q) {
+            for (uint32_t q = 0; q < GROUP; ++q) {
                 const uint32_t G = G0 + q;
                 if (G >= lo && G < hi) {
                     if (G > lo) {
@@ -543,11 +547,12 @@ __global__ void __launch_bounds__(EMIT_THREADS, TPDCU_EMIT_MINB) emit_kernel(Emi
                     key[q] = ((uint64_t)(((row + rx) << ds.extra) | (wd >> 16)) << 32) | id;
                 }
             }
-            if (lo == G0 && hi == G0 + 4u && G0 + 4u <= a.capacity) {
-                stg256(a.keys + G0, key[0], key[1], key[2], key[3]);
+            if (lo == G0 && hi == G0 + GROUP && G0 + GROUP <= a.capacity) {
+#pragma unroll
+                for (uint32_t q = 0; q < GROUP; q += 4) stg256(a.keys + G0 + q, key[q], key[q + 1], key[q + 2], key[q + 3]);
             } else {
 #pragma unroll
-                for (uint32_t q = 0; q < 4; ++q) {
+                for (uint32_t q = 0; q < GROUP; ++q) {
                     const uint32_t G = G0 + q;
                     if (G >= lo && G < hi && G < a.capacity) a.keys[G] = key[q];
                 }
