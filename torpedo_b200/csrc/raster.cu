@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
     // and a round only waits for the gather that depends on the cull: the survivors' rows. (Measured and discarded for
     // those: one cp.async.bulk per survivor into shared memory behind a per-warp mbarrier — 128 small TMA copies per round
     // are no faster than the loads and cost a CTA per SM in shared memory (0.349 ms); the SH degree as a template parameter
-    // (0.353 ms); prefetch.global.L2 of the survivors' rows at cull time (0.373 ms against 0.342 ms).)
+    // (0.353 ms); prefetch.global.L2 of the survivors' rows at cull time (0.373 ms against 0.342 ms); four fill warps + four drain
+    // warps per tile with a double-buffered queue behind mbarriers (profiles/experiments/blend_ws_kernel.cuh: 0.343-0.416 ms).)
     uint32_t g_cur = 0, g_next = 0;
     float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
     if (in + tid < range.y) g_cur = (uint32_t)__ldg(words + in + tid);
