@@ -180,9 +180,10 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
                 const uint32_t c = p == 0 ? (chains > 1 ? c_first + (j >= c_change ? 1u : 0u) : 0u) : ((uint32_t)(k[j] >> seg_shift) & seg_mask);
                 return row_base + (c << SORT_RADIX_BITS) + hist_slot(d);   // bank swizzle: the tile sort's low digits sit at stride 4
             };
-            if (valid == HIST_KPT && p == 0 && kind == SORT_KIND_TILE) {
-                // the pairs' low tile bits change with every element (a Gaussian's tiles are emitted row by row): no runs to
-                // encode, one counting atomic per element is cheaper than looking for them
+            if (valid == HIST_KPT && (kind == SORT_KIND_DEPTH || (p == 0 && kind == SORT_KIND_TILE))) {
+                // depth bits of neighbours in index order are unrelated, and the pairs' low tile bits change with every element
+                // (a Gaussian's tiles are emitted row by row): no runs to encode, one counting atomic per element is cheaper
+                // than looking for them
 #pragma unroll
                 for (uint32_t j = 0; j < HIST_KPT; ++j)
                     asm volatile("red.shared.add.u32 [%0], 1;" : : "r"(h_s + 4u * slot(j)) : "memory");
