@@ -11,8 +11,14 @@
 // of the word, so the result is exactly the reference's stable sort of (tile << 32 | depth, index) pairs, for
 // 8 + 2 * 16 B of traffic per pair instead of 8 + 5 * 16 + 4.
 //
-// Element counts live in device memory (FrameCtl): the host never learns them inside a frame, grids are sized by the
-// buffer capacities and surplus CTAs exit on their ticket. The standalone API sorts caller-provided (u64, u32) pairs.
+// Element counts live in device memory (FrameCtl): the host never learns them inside a frame; the pass kernel is persistent
+// (as many CTAs as stay resident, tiles drawn by ticket) and a pass the frame does not need exits at once. The standalone API
+// sorts caller-provided (u64, u32) pairs with the same kernels.
+//
+// What makes a pass fast here (DESIGN.md §4 has the measurements): ranking by returning shared-memory atomics (one
+// instruction per key), bank-swizzled per-warp counters, look-back CHAINS — the input of a pass is cut into SORT_CHAINS segments
+// whose digit counts the histogram kernel provides up front, so every segment runs its own shallow decoupled look-back —
+// persistent CTAs that load their next tile while they write the current one out, and half-size tiles for the end of a pass.
 #include "common.cuh"
 
 #include <algorithm>
