@@ -400,12 +400,12 @@ def run_gpu(args):
             "sort_gkeys_per_s": stage_pairs / (sort_ms * 1e-3) / 1e9 if sort_ms > 0 else None,
             "sort": dict(sort_info, design="two-level: visible Gaussians by depth, duplication in depth order, pairs by tile",
                          bytes_per_pair=8 + 16 * passes, bytes_per_visible_gaussian=8 + 16 * depth_passes),
-            # share of one frame alone per stage, and what bounds it (ncu: profiles/r1_s3_ncu_*.txt). The blend is the largest
+            # share of one frame alone per stage, and what bounds it (ncu: profiles/r2_ncu_frame_kernels.txt). The blend is the largest
             # stage and is bound by SM issue slots and L1 gathers, not by HBM or tensor throughput; the roofline object below
             # is therefore about the largest HBM-bound kernel, the onesweep pass (6 launches, a quarter of the frame).
             "stage_shares": {k: round(stages[k] / stages["frame"], 3) for k in ("preprocess", "depth_sort", "duplicate", "tile_sort", "ranges", "blend")},
-            "stage_bounds": {"preprocess": "issue / barrier (HBM 35 %)", "depth_sort": "latency (L2-resident, two waves of tiles)", "duplicate": "latency / LSU",
-                             "tile_sort": "hbm (onesweep passes) + smem atomics (histogram)", "ranges": "hbm", "blend": "SM issue + L1 gathers (on-demand SH colour inside)"},
+            "stage_bounds": {"preprocess": "issue 60 % / HBM 49 % (the bit-exact chain is unfused fp32)", "depth_sort": "latency (L2-resident, two tiles per resident CTA)", "duplicate": "latency / LSU",
+                             "tile_sort": "L1 data pipe 65-68 % (shared-memory wavefronts of ranking and scatter), HBM 40 %; histogram: issue", "ranges": "hbm", "blend": "SM issue 61 % + L1 gathers (on-demand SH colour inside)"},
             "roofline": {"kernel": "onesweep_kernel<WORDS> (one 8-bit digit pass of the tile sort over the pair words; average over the passes of a frame)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pass_ms,

@@ -7,7 +7,7 @@
 //     launches are sized by the grow-only pair capacity and an overflowing frame is re-rendered lazily;
 //   * a two-level sort: the visible Gaussians by depth, duplication in that order, then the pairs by tile only (sort.cu)
 //     instead of one 23-pass sort of every pair (GaussianEngine.cpp:822-841);
-//   * 17 launches per frame (replayed from a CUDA graph) instead of 2 + 1 + 92 + 2 dispatches with 95 pipeline
+//   * 14 launches per frame at 1080p (12 of them replayed from a CUDA graph) instead of 2 + 1 + 92 + 2 dispatches with 95 pipeline
 //     barriers (GaussianEngine.cpp:777-863);
 //   * several frames in flight, like the reference's Frame objects (GaussianEngine.h:104-117, SurfaceRenderer.h:66): every
 //     frame slot owns its splat arrays, pair buffers and a private stream, so the memory-bound front of frame k+1
