@@ -519,7 +519,11 @@ __global__ void __launch_bounds__(EMIT_THREADS, TPDCU_EMIT_MINB) emit_kernel(Emi
             uint32_t wd = sw[g], xy = sxy[g], id = sid[g];
             uint32_t w = wd & 0xffffu;
             const uint32_t r = j - off[g];
-            const uint32_t ry = r / w;
+            // r / w without the integer-division sequence: the quotient is a row of the rectangle (< 65536), so the float
+            // quotient is off by at most one
+            uint32_t ry = (uint32_t)__fdividef((float)r, (float)w);
+            if (ry * w > r) --ry;
+            else if ((ry + 1u) * w <= r) ++ry;
             uint32_t rx = r - ry * w;
             uint32_t row = ((xy >> 16) + ry) * gx + (xy & 0xffffu);  // tile id of the rectangle's column 0 in the current row
             uint32_t next_off = g + 1 < EMIT_PART ? off[g + 1] : 0xffffffffu;
