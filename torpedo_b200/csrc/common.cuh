@@ -18,6 +18,9 @@ constexpr uint32_t SH_PLANES = 12;        // 48 SH floats = 12 float4 per Gaussi
 constexpr uint32_t SORT_RADIX_BITS = 8;
 constexpr uint32_t SORT_BINS = 1u << SORT_RADIX_BITS;
 constexpr uint32_t SORT_MAX_PASSES = 8;   // 64-bit keys
+#ifndef TPDCU_PDL
+#define TPDCU_PDL 1
+#endif
 #ifndef TPDCU_SORT_KPT
 #define TPDCU_SORT_KPT 32
 #endif
@@ -153,6 +156,23 @@ struct SceneArrays {
 constexpr uint32_t FLAG_INVALID = 0u;
 constexpr uint32_t FLAG_AGGREGATE = 1u;
 constexpr uint32_t FLAG_PREFIX = 2u;
+
+// Programmatic dependent launch (PDL). A kernel launched with pdl_launch() may become resident while its predecessor in the
+// stream is still draining: pdl_wait() — the first statement of every kernel — holds it until the predecessor has completed and
+// its writes are visible, and is a no-op for a kernel that was launched the ordinary way. pdl_release() lets the NEXT kernel of
+// the stream be scheduled as soon as this grid's CTAs have all started: its blocks then take the SM slots this grid's last
+// CTAs free one by one, instead of paying a launch and a ramp-up after the last of them has gone (a few microseconds per kernel
+// boundary, fourteen boundaries per frame).
+__device__ __forceinline__ void pdl_wait() {
+#if TPDCU_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_release() {
+#if TPDCU_PDL
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 
 __device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
     uint64_t v;
@@ -363,6 +383,19 @@ uint32_t emit_parts(uint32_t n);  // duplication partitions (one scan descriptor
 // introspection: the reference's unsorted (key, value) buffers, in the reference's (index) order
 cudaError_t launch_export_unsorted(const SplatArrays& a, uint32_t n, uint32_t width, uint64_t* keys, uint32_t* vals, uint32_t capacity,
                                    cudaStream_t s);
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute (see pdl_wait): the kernel may be scheduled before its
+// predecessor in the stream has finished
+template <typename... KArgs, typename... Args>
+inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = TPDCU_PDL ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 struct SortLaunch {
     uint64_t* keys[2];                    // pair keys, or words

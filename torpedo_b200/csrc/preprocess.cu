@@ -265,6 +265,8 @@ __device__ __forceinline__ Projected project_one(const PreprocessLaunch& a, uint
 // goes on with the next partition, and only then resolves the previous one's prefix: every predecessor has published by then,
 // and as every CTA defers alike the distance to the nearest PREFIX stays what it was.
 __global__ void __launch_bounds__(PRE_THREADS, TPDCU_PRE_MINB) preprocess_kernel(PreprocessLaunch a) {
+    pdl_wait();      // (its predecessor in the stream is a memset: a no-op) ...
+    pdl_release();   // ... but the depth sort's histogram kernel may be scheduled as this grid's CTAs leave
     __shared__ uint32_t s_part;
     __shared__ uint64_t s_base;                 // exclusive (visible, pairs) prefix of the partition being completed
     __shared__ float s_vm[16], s_pm[16], s_v[12], s_focal[2];
@@ -465,6 +467,8 @@ constexpr uint32_t EMIT_PART = EMIT_THREADS * EMIT_ITEMS;
 // resolves the look-back of its previous partition and emits that partition's pairs — by then every predecessor has published
 // (ncu before: barrier stall 7.9 warps per issue behind the one-warp look-back).
 __global__ void __launch_bounds__(EMIT_THREADS, TPDCU_EMIT_MINB) emit_kernel(EmitLaunch a) {
+    pdl_wait();
+    pdl_release();
     __shared__ uint32_t s_part;
     __shared__ uint64_t s_base;
     __shared__ uint32_t s_off[2][EMIT_PART];    // exclusive pair offsets inside the partition     [parity of the CTA's turn]
@@ -639,7 +643,7 @@ cudaError_t launch_emit(const EmitLaunch& a, cudaStream_t s) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sm_count = 148;
     }
-    emit_kernel<<<std::min<uint32_t>(emit_parts(a.n), (uint32_t)sm_count * TPDCU_EMIT_MINB), EMIT_THREADS, 0, s>>>(a);
+    pdl_launch(emit_kernel, std::min<uint32_t>(emit_parts(a.n), (uint32_t)sm_count * TPDCU_EMIT_MINB), EMIT_THREADS, 0, s, a);
     return cudaGetLastError();
 }
 

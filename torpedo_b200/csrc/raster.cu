@@ -13,6 +13,8 @@ namespace tpdcu {
 // ---------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) ranges_kernel(RasterLaunch a) {
+    pdl_wait();
+    pdl_release();
     const uint32_t n = a.plan->n;
     const uint64_t* __restrict__ keys = a.plan->final_sel ? a.keys[1] : a.keys[0];
     const uint32_t tshift = 32u + a.plan->tile_shift;  // words are (tile << shift | top depth bits) << 32 | Gaussian index
@@ -74,6 +76,7 @@ __device__ __forceinline__ uint32_t order_bucket(uint32_t len) {
 }
 
 __global__ void __launch_bounds__(ORDER_THREADS) tile_order_kernel(RasterLaunch a, uint32_t tiles) {
+    pdl_wait();
     __shared__ uint32_t s_off[ORDER_BUCKETS];
     __shared__ uint32_t s_warp[ORDER_BUCKETS / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -132,9 +135,9 @@ cudaError_t launch_ranges(const RasterLaunch& a, uint32_t capacity, cudaStream_t
         uint32_t grid = (capacity / 4 + 256) / 256;
         const uint32_t cap = (uint32_t)(a.sm_count > 0 ? a.sm_count : 148) * 8u;
         if (grid > cap) grid = cap;
-        ranges_kernel<<<grid, 256, 0, s>>>(a);
+        pdl_launch(ranges_kernel, grid, 256, 0, s, a);
     }
-    if (tiles != 0) tile_order_kernel<<<1, ORDER_THREADS, 0, s>>>(a, tiles);
+    if (tiles != 0) pdl_launch(tile_order_kernel, 1, ORDER_THREADS, 0, s, a, tiles);
     return cudaGetLastError();
 }
 

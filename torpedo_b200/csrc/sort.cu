@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(HIST_THREADS) sort_hist_kernel(const uint64_t*
                                                                   SortPlan* plan, uint32_t kind, uint32_t n_host, uint32_t capacity,
                                                                   uint32_t end_bit, uint32_t tile_bits) {
     __shared__ uint32_t h[SORT_CHAIN_ROWS * SORT_BINS];
+    pdl_wait();
+    pdl_release();
     const SortSpec sp = sort_spec(frame, kind, n_host, capacity, end_bit, tile_bits);
     const uint32_t n = sp.n, num_passes = passes_needed(sp.total_bits);
     const uint32_t chains = chains_of(kind), rows = num_passes * chains;
@@ -380,6 +382,8 @@ onesweep_kernel(uint64_t* keys0, uint64_t* keys1, uint32_t* vals0, uint32_t* val
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
+    pdl_wait();
+    pdl_release();
     if (plan->skip[pass]) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) sm.part = atomicAdd(&ctl->ticket[pass], 1u);
@@ -785,8 +789,8 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     // every CTA adds up to passes x segments x 256 counters to the global histograms: few, fat CTAs
     const uint32_t hist_max = (uint32_t)a.sm_count * (a.kind == SORT_KIND_DEPTH ? TPDCU_HIST_CTAS_DEPTH : TPDCU_HIST_CTAS_TILE);
     if (hist_grid > hist_max) hist_grid = hist_max;
-    if (words) sort_hist_kernel<true><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
-    else sort_hist_kernel<false><<<hist_grid, HIST_THREADS, 0, s>>>(a.keys[0], a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
+    if (words) pdl_launch(sort_hist_kernel<true>, hist_grid, HIST_THREADS, 0, s, (const uint64_t*)a.keys[0], (const FrameCtl*)a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
+    else pdl_launch(sort_hist_kernel<false>, hist_grid, HIST_THREADS, 0, s, (const uint64_t*)a.keys[0], (const FrameCtl*)a.frame, a.ctl, a.plan, a.kind, n_host, a.capacity, a.end_bit, a.tile_bits);
     if (ev_after_plan) cudaEventRecord(ev_after_plan, s);
     const uint32_t parts = sort_parts(bound, a.kind);
     const uint32_t parts_cap = sort_parts(a.capacity, a.kind);
@@ -795,9 +799,9 @@ cudaError_t launch_sort(const SortLaunch& a, uint32_t n_host, cudaStream_t s, cu
     for (uint32_t p = 0; p < num_passes; ++p) {
         uint32_t* lb = a.lookback + (size_t)p * parts_cap * SORT_BINS;
         if (words)
-            onesweep_kernel<MODE_WORDS><<<std::min(parts, resident), SORT_THREADS, sizeof(OnesweepSmem<MODE_WORDS>), s>>>(a.keys[0], a.keys[1], nullptr, nullptr, a.ctl, a.plan, lb, p);
+            pdl_launch(onesweep_kernel<MODE_WORDS>, std::min(parts, resident), SORT_THREADS, sizeof(OnesweepSmem<MODE_WORDS>), s, a.keys[0], a.keys[1], (uint32_t*)nullptr, (uint32_t*)nullptr, a.ctl, (const SortPlan*)a.plan, lb, p);
         else
-            onesweep_kernel<MODE_PAIRS><<<std::min(parts, resident), SORT_THREADS, sizeof(OnesweepSmem<MODE_PAIRS>), s>>>(a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, a.plan, lb, p);
+            pdl_launch(onesweep_kernel<MODE_PAIRS>, std::min(parts, resident), SORT_THREADS, sizeof(OnesweepSmem<MODE_PAIRS>), s, a.keys[0], a.keys[1], a.vals[0], a.vals[1], a.ctl, (const SortPlan*)a.plan, lb, p);
     }
     return cudaGetLastError();
 }
