@@ -428,7 +428,7 @@ def run_gpu(args):
     eng.close()
     del frames, gathered
     torch.cuda.empty_cache()
-    config5 = None if args.no_config5 else run_config5(E, torch, dist, world, rank, local_rank, dev)
+    config5 = None if args.no_config5 else run_config5(E, torch, dist, world, rank, local_rank, dev, args.config5_collect)
     if rank == 0:
         line["config5"] = config5
         emit(line)
@@ -437,10 +437,12 @@ def run_gpu(args):
     return 0
 
 
-def run_config5(E, torch, dist, world, rank, local_rank, dev):
+def run_config5(E, torch, dist, world, rank, local_rank, dev, mode="direct"):
     """BASELINE.json configs[4]: a 64-view batch of a 3 M-Gaussian scene at 1080p, views sharded round-robin over the ranks,
-    scene replicated with one NCCL broadcast, frames gathered on rank 0 straight into view order (torpedo_b200.multiview).
-    STRONG scaling: the batch is fixed, N grows. Returns the sub-object on rank 0 (max-over-ranks device time)."""
+    scene replicated with one NCCL broadcast. STRONG scaling: the batch is fixed, N grows. Two ways of collecting the frames on
+    rank 0 (torpedo_b200.multiview): "direct" — every rank's blend kernel stores its pixels straight into rank 0's frame array
+    over NVLink (CUDA IPC mapping, set up once like the scene broadcast), one stream-ordered fence per batch; "gather" — render
+    locally, one NCCL gather per view slot in asynchronous chunks. Returns the sub-object on rank 0 (max-over-ranks device time)."""
     from torpedo_b200 import multiview as mv
     from torpedo_b200 import scenes
     n, views, radius, chunk = 3_000_000, 64, 5.0, 2
@@ -461,23 +463,35 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev):
     from torpedo_b200._lib import check, tpdcu
     lib = tpdcu()
 
-    def render_batch(view_ids, out):
-        # asynchronous: every view is enqueued behind the previous one (three frames in flight inside the engine) and the
-        # gather of a chunk is ordered behind its frames on the stream; the host only waits at the end of the batch
-        for k, v in enumerate(view_ids):
-            check(lib.tpdcu_bind_output_device_ptr(eng.ctx, out[k].data_ptr(), WIDTH * 4))
+    def render_to(view_ids, ptrs):
+        # asynchronous: every view is enqueued behind the previous one (three frames in flight inside the engine) and whatever
+        # follows (fence or gather) is ordered behind the frames on the stream; the host only waits at the end of the batch
+        for v, p in zip(view_ids, ptrs):
+            check(lib.tpdcu_bind_output_device_ptr(eng.ctx, p, WIDTH * 4))
             eng.raster_ubo(ubos[v], SH_DEGREE, stream)
+
+    def render_batch(view_ids, out):
+        render_to(view_ids, [out[k].data_ptr() for k in range(len(view_ids))])
+
+    shared = mv.SharedFrames(views, HEIGHT, WIDTH, local_rank) if mode == "direct" else None
+
+    def batch():
+        if shared is not None:
+            mv.render_views_direct(render_to, shared)
+            return shared.tensor() if rank == 0 else None
+        return mv.render_views(render_batch, views, HEIGHT, WIDTH, dev, chunk=chunk)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    check(lib.tpdcu_bind_output_device_ptr(eng.ctx, None, 0))
     for v in range(rank, views, world):                  # warm-up: pair buffers grow to the largest view of this rank
         eng.raster_ubo(ubos[v], SH_DEGREE, stream)
         eng.finish()
     for _ in range(2):
-        mv.render_views(render_batch, views, HEIGHT, WIDTH, dev, chunk=chunk)
+        batch()
         eng.finish()
     repeats_before = eng.frames_repeated()
     times, frames = [], None
@@ -485,7 +499,7 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        frames = mv.render_views(render_batch, views, HEIGHT, WIDTH, dev, chunk=chunk)
+        frames = batch()
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -498,11 +512,17 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev):
     if rank == 0:
         ms = statistics.median(times)
         nonblack = [int((frames[v, ::8, ::8, :3].amax() > 0).item()) for v in range(views)]
-        out = {"workload": "64-view batch of 3M Gaussians at 1080p sharded by view across N B200 with NCCL frame gather", "n_gaussians": n,
+        how = ("every rank's blend kernel stores its pixels straight into rank 0's frame array over NVLink (CUDA IPC mapping made once, "
+               "outside the timed region, like the scene broadcast); one stream-ordered NCCL fence per batch" if mode == "direct" else
+               f"one NCCL gather per view slot straight into view order, {chunk} slots per asynchronous chunk")
+        out = {"workload": "64-view batch of 3M Gaussians at 1080p sharded by view across N B200, frames collected on rank 0", "n_gaussians": n,
                "views": views, "n_gpus": world, "scaling": "strong", "ms_per_batch": ms, "ms_per_view": ms / views, "views_per_s": views / ms * 1e3,
-               "batches_timed": len(times), "gather": f"one NCCL gather per view slot straight into view order, {chunk} slots per asynchronous chunk",
+               "batches_timed": len(times), "collect": mode, "gather": how,
                "frames_repeated": repeated, "views_with_pixels": sum(nonblack),
-               "limiter_at_n8": "8 views per GPU are a ~3.8 ms job plus the fill and drain of the three-frame pipeline; rank 0 ingests 56 x 8.29 MB = 465 MB over NVLink behind them"}
+               "limiter_at_n8": "8 views per GPU are a ~3.8 ms job plus the fill and drain of the three-frame pipeline"}
+    frames = None
+    if shared is not None:
+        shared.close()
     eng.close()
     return out
 
@@ -531,6 +551,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the 64-view x 3M multi-view batch (BASELINE configs[4]) sub-object")
+    ap.add_argument("--config5-collect", default="direct", choices=["direct", "gather"],
+                    help="how the multi-view batch's frames reach rank 0: blend stores over NVLink into rank 0's array, or NCCL gathers")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

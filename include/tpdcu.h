@@ -79,6 +79,21 @@ int tpdcu_bind_output_device_ptr(tpdcu_ctx* ctx, void* d_rgba8, size_t pitch_byt
  * source (GaussianEngine.cpp:865-875). The fd is consumed on success. Linear RGBA8, tightly packed. */
 int tpdcu_bind_output_fd(tpdcu_ctx* ctx, int fd, size_t bytes);
 
+/* ---- frames of several GPUs collected in one GPU's memory (no reference counterpart: the reference is
+ * one GPU, one target, GaussianEngine.cpp:315-333) -------------------------------------------------------------------
+ * Views of a batch are sharded over one process per GPU; instead of rendering locally and gathering afterwards, every
+ * process binds (tpdcu_bind_output_device_ptr) its views' slots of ONE frame array that lives in the collecting GPU's
+ * HBM and is mapped into all of them with CUDA IPC: the blend kernel's pixel stores travel over NVLink / NVSwitch as
+ * they are produced and no copy or collective follows the frame. The creator owns the allocation; the other processes
+ * of the box open the 64-byte handle (peer access is enabled on first use). A process cannot open its own handle.
+ * Completion across processes is the callers' business (a stream-ordered collective or a host barrier after
+ * tpdcu_finish). */
+#define TPDCU_IPC_HANDLE_BYTES 64
+int tpdcu_ipc_frames_create(int device, size_t bytes, void** d_frames, unsigned char handle[TPDCU_IPC_HANDLE_BYTES]);
+int tpdcu_ipc_frames_open(int device, const unsigned char handle[TPDCU_IPC_HANDLE_BYTES], void** d_frames);
+int tpdcu_ipc_frames_close(int device, void* d_frames);   /* a mapping made by tpdcu_ipc_frames_open */
+int tpdcu_ipc_frames_destroy(int device, void* d_frames); /* an allocation made by tpdcu_ipc_frames_create */
+
 /* ---- per-frame hot path: GaussianEngine::rasterFrame (GaussianEngine.cpp:621-712) -------------- */
 
 /* One frame: camera upload (updateCameraBuffer :764-775) -> geometry + scan (project.slang, prefix.slang)

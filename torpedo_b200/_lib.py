@@ -28,6 +28,10 @@ TPDCU_SYMBOLS = {
     "tpdcu_resize": (i32, [vp, u32, u32]),
     "tpdcu_bind_output_device_ptr": (i32, [vp, vp, sz]),
     "tpdcu_bind_output_fd": (i32, [vp, i32, sz]),
+    "tpdcu_ipc_frames_create": (i32, [i32, sz, C.POINTER(vp), vp]),
+    "tpdcu_ipc_frames_open": (i32, [i32, vp, C.POINTER(vp)]),
+    "tpdcu_ipc_frames_close": (i32, [i32, vp]),
+    "tpdcu_ipc_frames_destroy": (i32, [i32, vp]),
     "tpdcu_raster": (i32, [vp, vp, u32, vp]),
     "tpdcu_raster_views": (i32, [vp, vp, u32, u32, vp, sz, vp]),
     "tpdcu_finish": (i32, [vp, C.POINTER(u32)]),

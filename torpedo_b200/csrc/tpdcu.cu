@@ -824,6 +824,53 @@ int tpdcu_bind_output_fd(tpdcu_ctx* c, int fd, size_t bytes) {
     return TPDCU_OK;
 }
 
+// ---- one frame array in the collecting GPU's memory, mapped into every process of the box (tpdcu.h) ------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == TPDCU_IPC_HANDLE_BYTES, "the ABI passes the CUDA IPC handle as 64 opaque bytes");
+
+int tpdcu_ipc_frames_create(int device, size_t bytes, void** d_frames, unsigned char handle[TPDCU_IPC_HANDLE_BYTES]) {
+    if (!d_frames || !handle || bytes == 0) return fail(TPDCU_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(device));
+    void* p = nullptr;
+    CK(cudaMalloc(&p, bytes));   // a whole allocation of its own: the handle names the allocation, not an offset into one
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        cudaGetLastError();
+        return fail(TPDCU_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, sizeof(h));
+    *d_frames = p;
+    return TPDCU_OK;
+}
+
+int tpdcu_ipc_frames_open(int device, const unsigned char handle[TPDCU_IPC_HANDLE_BYTES], void** d_frames) {
+    if (!d_frames || !handle) return fail(TPDCU_ERR_INVALID, "bad arguments");
+    CK(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_frames = p;
+    return TPDCU_OK;
+}
+
+int tpdcu_ipc_frames_close(int device, void* d_frames) {
+    if (!d_frames) return TPDCU_OK;
+    CK(cudaSetDevice(device));
+    CK(cudaDeviceSynchronize());   // no kernel of this process may still be storing into the mapping
+    CK(cudaIpcCloseMemHandle(d_frames));
+    return TPDCU_OK;
+}
+
+int tpdcu_ipc_frames_destroy(int device, void* d_frames) {
+    if (!d_frames) return TPDCU_OK;
+    CK(cudaSetDevice(device));
+    CK(cudaFree(d_frames));
+    return TPDCU_OK;
+}
+
 int tpdcu_raster(tpdcu_ctx* c, const float camera_ubo[TPDCU_CAMERA_FLOATS], uint32_t sh_degree, void* stream) {
     if (int r = check_ready(c)) return r;
     if (!camera_ubo) return fail(TPDCU_ERR_INVALID, "camera_ubo is null");

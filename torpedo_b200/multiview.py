@@ -104,3 +104,84 @@ def render_views(render_batch: Callable[[Sequence[int], torch.Tensor], None], n_
     for work in pending or []:
         work.wait()
     return out[:n_views] if rank == dst else None
+
+
+class SharedFrames:
+    """The batch's (n_views, H, W, 4) uint8 frame array, living in `dst`'s HBM and mapped into every rank of the box.
+
+    The gather above costs the collecting GPU twice: NCCL's receive kernels take SMs away from its own views, and the last
+    chunk's transfer trails the last frame. Here nothing is gathered: rank r binds slot v of this array as the render target
+    of its view v (`ptr_of_view`), the blend kernel's pixel stores cross NVLink / NVSwitch as they are produced, and the only
+    collective left is the completion fence. Set up once per (batch shape, process group) — an IPC handle exchange and a
+    peer mapping — like the scene broadcast; `include/tpdcu.h` (tpdcu_ipc_frames_*) is the ABI underneath.
+    """
+
+    def __init__(self, n_views: int, height: int, width: int, device_index: int, dst: int = 0):
+        import ctypes as C
+
+        from ._lib import check, tpdcu
+        self._lib, self._check = tpdcu(), check
+        self.world, self.rank = _world_rank()
+        self.n_views, self.height, self.width, self.dst, self.device_index = n_views, height, width, dst, device_index
+        self.frame_bytes = height * width * 4
+        self.owner = self.rank == dst
+        self._ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        if self.owner:
+            check(self._lib.tpdcu_ipc_frames_create(device_index, n_views * self.frame_bytes, C.byref(self._ptr), handle))
+        box = [bytes(handle)]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=dst)
+        if not self.owner:
+            raw = (C.c_ubyte * 64).from_buffer_copy(box[0])
+            check(self._lib.tpdcu_ipc_frames_open(device_index, raw, C.byref(self._ptr)))
+        self._fence = None
+
+    def ptr_of_view(self, view: int) -> int:
+        if not (0 <= view < self.n_views):
+            raise IndexError(view)
+        return self._ptr.value + view * self.frame_bytes
+
+    def fence(self) -> None:
+        """Returns (stream-ordered on NCCL, host-ordered otherwise) once every rank's frames of the batch are in the array."""
+        if self.world == 1:
+            return
+        if dist.get_backend() == "nccl":
+            if self._fence is None:
+                self._fence = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", self.device_index))
+            dist.all_reduce(self._fence)     # queued behind this rank's frames on the current stream
+        else:
+            torch.cuda.synchronize(self.device_index)
+            dist.barrier()
+
+    def tensor(self) -> torch.Tensor:
+        """The frames as a torch tensor (collecting rank only; the other ranks hold a peer mapping, not local memory)."""
+        if not self.owner:
+            raise RuntimeError("only the collecting rank can read the frames")
+        shape = (self.n_views, self.height, self.width, 4)
+        iface = {"shape": shape, "typestr": "|u1", "data": (self._ptr.value, False), "version": 3, "strides": None}
+        holder = type("_Frames", (), {"__cuda_array_interface__": iface, "_keep": self})()
+        return torch.as_tensor(holder, device=torch.device("cuda", self.device_index))
+
+    def close(self) -> None:
+        if self._ptr.value:
+            if self.world > 1:
+                self.fence()
+                torch.cuda.synchronize(self.device_index)
+                if dist.get_backend() == "nccl":
+                    dist.barrier()
+            if self.owner:
+                self._check(self._lib.tpdcu_ipc_frames_destroy(self.device_index, self._ptr))
+            else:
+                self._check(self._lib.tpdcu_ipc_frames_close(self.device_index, self._ptr))
+            self._ptr.value = None
+
+
+def render_views_direct(render_to: Callable[[Sequence[int], Sequence[int]], None], shared: SharedFrames) -> None:
+    """Shard the views like `render_views`, but let `render_to(view_ids, target_ptrs)` render each view straight into its slot
+    of the shared frame array; ends with the completion fence. On return (stream-ordered on NCCL) `shared.tensor()` on the
+    collecting rank holds the batch in view order."""
+    mine = views_of_rank(shared.n_views, shared.rank, shared.world)
+    if mine:
+        render_to(mine, [shared.ptr_of_view(v) for v in mine])
+    shared.fence()
