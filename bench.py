@@ -437,12 +437,15 @@ def run_gpu(args):
     return 0
 
 
-def run_config5(E, torch, dist, world, rank, local_rank, dev, mode="direct"):
+def run_config5(E, torch, dist, world, rank, local_rank, dev, mode="push"):
     """BASELINE.json configs[4]: a 64-view batch of a 3 M-Gaussian scene at 1080p, views sharded round-robin over the ranks,
-    scene replicated with one NCCL broadcast. STRONG scaling: the batch is fixed, N grows. Two ways of collecting the frames on
-    rank 0 (torpedo_b200.multiview): "direct" — every rank's blend kernel stores its pixels straight into rank 0's frame array
-    over NVLink (CUDA IPC mapping, set up once like the scene broadcast), one stream-ordered fence per batch; "gather" — render
-    locally, one NCCL gather per view slot in asynchronous chunks. Returns the sub-object on rank 0 (max-over-ranks device time)."""
+    scene replicated with one NCCL broadcast. STRONG scaling: the batch is fixed, N grows. Three ways of collecting the frames on
+    rank 0 (torpedo_b200.multiview), all measured at N = 8 in one run (profiles/r2_collect_modes.jsonl): "push" (default) —
+    render locally, a copy engine pushes every finished frame into its slot of rank 0's frame array over NVLink (CUDA IPC
+    mapping, set up once like the scene broadcast), one stream-ordered fence per batch: 16.5 k views/s; "gather" — one NCCL
+    gather per view slot in asynchronous chunks, whose receive kernels take SMs from rank 0's own views: 15.5 k; "direct" — the
+    blend kernel stores its pixels straight into rank 0's array: 13.7 k (seven GPUs' 32-byte stores into one stall the senders).
+    Returns the sub-object on rank 0 (max-over-ranks device time)."""
     from torpedo_b200 import multiview as mv
     from torpedo_b200 import scenes
     n, views, radius, chunk = 3_000_000, 64, 5.0, 2
@@ -470,14 +473,29 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev, mode="direct"):
             check(lib.tpdcu_bind_output_device_ptr(eng.ctx, p, WIDTH * 4))
             eng.raster_ubo(ubos[v], SH_DEGREE, stream)
 
+    def push_to(view_ids, ptrs):
+        # render into the engine's own targets (local HBM) and let a copy engine push each finished frame into its slot of
+        # rank 0's array: whole 8.29 MB transfers over NVLink, no SM on either side, overlapped with the next frames
+        check(lib.tpdcu_bind_output_device_ptr(eng.ctx, None, 0))
+        for v, p in zip(view_ids, ptrs):
+            eng.raster_ubo(ubos[v], SH_DEGREE, stream)
+            check(lib.tpdcu_read_frame_async(eng.ctx, p, WIDTH * 4, stream))
+
     def render_batch(view_ids, out):
         render_to(view_ids, [out[k].data_ptr() for k in range(len(view_ids))])
 
-    shared = mv.SharedFrames(views, HEIGHT, WIDTH, local_rank) if mode == "direct" else None
+    shared = mv.SharedFrames(views, HEIGHT, WIDTH, local_rank) if mode in ("direct", "push") else None
+    mid = torch.cuda.Event(enable_timing=True)
+
+    def timed_render(fn):
+        def run(view_ids, ptrs):
+            fn(view_ids, ptrs)
+            mid.record()      # this rank's own frames are done here; what follows is the fence
+        return run
 
     def batch():
         if shared is not None:
-            mv.render_views_direct(render_to, shared)
+            mv.render_views_direct(timed_render(render_to if mode == "direct" else push_to), shared)
             return shared.tensor() if rank == 0 else None
         return mv.render_views(render_batch, views, HEIGHT, WIDTH, dev, chunk=chunk)
 
@@ -503,9 +521,15 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev, mode="direct"):
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        own = torch.tensor([e0.elapsed_time(mid) if shared is not None else 0.0], dtype=torch.float64, device=dev)
+        per_rank = [torch.zeros_like(own) for _ in range(world)]
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_gather(per_rank, own)
+        else:
+            per_rank = [own]
         times.append(float(t.item()))
+        rank_ms = [round(float(x.item()), 3) for x in per_rank]
     eng.finish()
     repeated = eng.frames_repeated() - repeats_before
     out = None
@@ -518,8 +542,9 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev, mode="direct"):
         out = {"workload": "64-view batch of 3M Gaussians at 1080p sharded by view across N B200, frames collected on rank 0", "n_gaussians": n,
                "views": views, "n_gpus": world, "scaling": "strong", "ms_per_batch": ms, "ms_per_view": ms / views, "views_per_s": views / ms * 1e3,
                "batches_timed": len(times), "collect": mode, "gather": how,
+               "own_frames_ms_per_rank_last_batch": rank_ms if shared is not None else None,
                "frames_repeated": repeated, "views_with_pixels": sum(nonblack),
-               "limiter_at_n8": "8 views per GPU are a ~3.8 ms job plus the fill and drain of the three-frame pipeline"}
+               "limiter_at_n8": "8 views per GPU are a 3.76 ms job at the one-GPU rate; the rest is the fill and drain of the three-frame pipeline and the fence"}
     frames = None
     if shared is not None:
         shared.close()
@@ -551,8 +576,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config5", action="store_true", help="skip the 64-view x 3M multi-view batch (BASELINE configs[4]) sub-object")
-    ap.add_argument("--config5-collect", default="direct", choices=["direct", "gather"],
-                    help="how the multi-view batch's frames reach rank 0: blend stores over NVLink into rank 0's array, or NCCL gathers")
+    ap.add_argument("--config5-collect", default="push", choices=["direct", "push", "gather"],
+                    help="how the multi-view batch's frames reach rank 0: copy-engine pushes or blend stores over NVLink into rank 0's array, or NCCL gathers")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -119,7 +119,9 @@ int tpdcu_read_frame(tpdcu_ctx* ctx, void* host_rgba8, size_t host_pitch_bytes);
 /* Same copy, enqueued on `stream` (the stream the frame was rastered with) without waiting: the caller synchronises with the
  * stream or an event of its own. With several frames in flight this lets frame k+1 start while frame k travels to the host —
  * the role the swap-chain fences play in the reference's loop (SurfaceRenderer.cpp:254-319). P is not looked at here: a frame
- * that overflowed its buffers is only repeated by the next tpdcu_finish; tpdcu_frames_repeated tells whether any was. */
+ * that overflowed its buffers is only repeated by the next tpdcu_finish; tpdcu_frames_repeated tells whether any was.
+ * The destination may also be device memory, e.g. a slot of another GPU's frame array (tpdcu_ipc_frames_open): the copy
+ * engine then pushes the frame over NVLink while the next one renders. */
 int tpdcu_read_frame_async(tpdcu_ctx* ctx, void* host_rgba8, size_t host_pitch_bytes, void* stream);
 /* Checks everything enqueued so far (like tpdcu_finish) and returns how many frames had to be rendered again since
  * tpdcu_create because they overflowed the grow-only pair buffers (warm-up frames, in practice). */

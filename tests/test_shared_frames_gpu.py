@@ -56,24 +56,42 @@ def _worker(rank, world, port, result_path):
         shared = mv.SharedFrames(N_VIEWS, H, W, 0)
         rendered = []
 
-        def render_to(view_ids, ptrs):
+        def render_to(view_ids, ptrs):       # the blend kernel's stores go straight into the (foreign) array
             for v, p in zip(view_ids, ptrs):
                 rendered.append(v)
                 check(lib.tpdcu_bind_output_device_ptr(eng.ctx, p, W * 4))
                 eng.raster_ubo(ubos[v], 3, stream)
             eng.finish()
 
-        for _ in range(2):   # the array is reused batch after batch
-            mv.render_views_direct(render_to, shared)
-        assert rendered == mv.views_of_rank(N_VIEWS, rank, world) * 2
-        if rank == 0:
-            got = shared.tensor().cpu().numpy()
+        def push_to(view_ids, ptrs):         # rendered locally, pushed by the copy engine (tpdcu_read_frame_async to device memory)
             check(lib.tpdcu_bind_output_device_ptr(eng.ctx, None, 0))
-            for v in range(N_VIEWS):
+            for v, p in zip(view_ids, ptrs):
+                rendered.append(v)
                 eng.raster_ubo(ubos[v], 3, stream)
-                want = eng.draw()
-                assert want[..., :3].max() > 0
-                assert np.array_equal(got[v], want), f"view {v} (rendered by rank {v % world})"
+                check(lib.tpdcu_read_frame_async(eng.ctx, p, W * 4, stream))
+            eng.finish()
+
+        want = None
+        for fn in (render_to, push_to):
+            rendered.clear()
+            for _ in range(2):   # the array is reused batch after batch
+                mv.render_views_direct(fn, shared)
+            assert rendered == mv.views_of_rank(N_VIEWS, rank, world) * 2
+            if rank == 0:
+                got = shared.tensor().cpu().numpy()
+                if want is None:
+                    check(lib.tpdcu_bind_output_device_ptr(eng.ctx, None, 0))
+                    want = []
+                    for v in range(N_VIEWS):
+                        eng.raster_ubo(ubos[v], 3, stream)
+                        want.append(eng.draw().copy())
+                for v in range(N_VIEWS):
+                    assert want[v][..., :3].max() > 0
+                    assert np.array_equal(got[v], want[v]), f"{fn.__name__}: view {v} (rendered by rank {v % world})"
+                shared.tensor().zero_()
+                torch.cuda.synchronize()
+            dist.barrier()
+        if rank == 0:
             with pytest.raises(IndexError):
                 shared.ptr_of_view(N_VIEWS)
             np.save(result_path, got)

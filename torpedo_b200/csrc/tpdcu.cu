@@ -925,8 +925,14 @@ int tpdcu_read_frame_async(tpdcu_ctx* c, void* host_rgba8, size_t host_pitch_byt
     if (!host_rgba8 || host_pitch_bytes < (size_t)c->width * 4) return fail(TPDCU_ERR_INVALID, "bad host buffer");
     if (!c->have_newest) return fail(TPDCU_ERR_STATE, "no frame has been rendered");
     // `stream` must be the stream the frame was rastered with (it already waits for the frame); no host synchronisation here
-    CK(cudaMemcpy2DAsync(host_rgba8, host_pitch_bytes, c->newest.out, c->newest.pitch, (size_t)c->width * 4, c->height,
-                         cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    // cudaMemcpyDefault: the destination may be host memory or device memory — in particular another GPU's frame array
+    // (tpdcu_ipc_frames_open), which a copy engine fills over NVLink while the SMs render the next frame
+    const size_t row = (size_t)c->width * 4;
+    if (host_pitch_bytes == row && c->newest.pitch == row)
+        CK(cudaMemcpyAsync(host_rgba8, c->newest.out, row * c->height, cudaMemcpyDefault, (cudaStream_t)stream));
+    else
+        CK(cudaMemcpy2DAsync(host_rgba8, host_pitch_bytes, c->newest.out, c->newest.pitch, row, c->height, cudaMemcpyDefault,
+                             (cudaStream_t)stream));
     FrameSlot& f = last(c);
     if (c->newest.out == f.target) {  // the next frame of this slot must not overwrite the target before the copy has read it
         CK(cudaEventRecord(f.read_done, (cudaStream_t)stream));
