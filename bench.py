@@ -6,8 +6,9 @@
 A "step" is one frame of the hot path (preprocess+scan -> depth sort of the visible Gaussians -> duplication -> tile sort of
 the pairs -> ranges -> blend). At N > 1
 (launched under torchrun, one rank per GPU) the Gaussian set is replicated with one NCCL broadcast, independent camera
-views are sharded round-robin across ranks (view = step * N + rank) and the finished frames are gathered on rank 0 with
-NCCL inside the timed region — weak scaling; `value` = max-over-ranks time / total frames.
+views are sharded round-robin across ranks (view = step * N + rank) and every finished frame is pushed, inside the timed
+region, into its slot of one frame array in rank 0's HBM (CUDA IPC mapping; a copy engine moves it over NVLink while the next
+frame renders; one stream-ordered fence per K steps) — weak scaling; `value` = max-over-ranks time / total frames.
 
 JSON keys beyond the base contract: `roofline` (the onesweep pass kernel of the tile sort against measured HBM peak), `cpu_baseline`
 (the CPU oracle on the host cores), `e2e` (camera on the host -> rasterFrame -> draw() into pinned host memory),
@@ -248,23 +249,26 @@ def run_gpu(args):
     K, W = args.steps, max(args.warmup, 3)
     frame_bytes = WIDTH * HEIGHT * 4
     frames = torch.zeros((K, HEIGHT, WIDTH, 4), dtype=torch.uint8, device=dev)
-    gathered = [torch.zeros_like(frames) for _ in range(world)] if (world > 1 and rank == 0) else None
     from torpedo_b200._lib import check, tpdcu
     lib = tpdcu()
-
-    GATHER_CHUNK = 4  # frames per asynchronous gather: the transfer of one chunk overlaps the rendering of the next
+    # N > 1: the K * N frames of a round are collected on rank 0, slot = step * N + rank of ONE array in rank 0's HBM that every
+    # rank has mapped (torpedo_b200.multiview.SharedFrames; the mapping is made here, once, like the scene broadcast)
+    shared = None
+    if world > 1:
+        from torpedo_b200 import multiview as mv
+        shared = mv.SharedFrames(K * world, HEIGHT, WIDTH, local_rank)
 
     def render_steps(first_step, count, gather=False):
-        pending = []
         for s in range(count):
             view = (first_step + s) * world + rank
-            check(lib.tpdcu_bind_output_device_ptr(eng.ctx, frames[s].data_ptr(), WIDTH * 4))
-            eng.raster_ubo(ubos[view % RING_VIEWS], SH_DEGREE, stream)
-            if gather and world > 1 and ((s + 1) % GATHER_CHUNK == 0 or s + 1 == count):
-                c0 = s + 1 - ((s % GATHER_CHUNK) + 1)
-                pending.append(dist.gather(frames[c0:s + 1], [gt[c0:s + 1] for gt in gathered] if rank == 0 else None, dst=0, async_op=True))
-        for work in pending:
-            work.wait()  # the current stream waits for the transfers; the host does not
+            if shared is None:
+                check(lib.tpdcu_bind_output_device_ptr(eng.ctx, frames[s].data_ptr(), WIDTH * 4))
+                eng.raster_ubo(ubos[view % RING_VIEWS], SH_DEGREE, stream)
+            else:   # rendered into the engine's own target, pushed by a copy engine while the next frame renders
+                eng.raster_ubo(ubos[view % RING_VIEWS], SH_DEGREE, stream)
+                check(lib.tpdcu_read_frame_async(eng.ctx, shared.ptr_of_view(s * world + rank), WIDTH * 4, stream))
+        if shared is not None and gather:
+            shared.fence()  # stream-ordered: behind it rank 0 holds every rank's frames of these steps
 
     ubos = [ubo_for(v) for v in range(RING_VIEWS)]
 
@@ -282,7 +286,7 @@ def run_gpu(args):
     eng.finish()
     barrier()
 
-    # ---- timed region: R back-to-back rounds of K frames per rank (+ the NCCL frame gather at N > 1) -------------------
+    # ---- timed region: R back-to-back rounds of K frames per rank (+ their collection on rank 0 at N > 1) -------------------
     # K frames are ~20 ms: one noisy neighbour or two clock samples would decide the headline. The K-step loop is therefore
     # repeated (R rounds, every round a different stretch of the camera ring) until the region between the two events holds
     # >= MIN_TIMED_S of device time; `value` is the mean over all R*K frames and `rounds` says how many there were.
@@ -391,7 +395,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_gaussians": n, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
                        "views": f"ring of {RING_VIEWS} cameras through the garden eye, view = step*N + rank",
-                       "parallelism": f"views sharded over {world} GPU(s), scene replicated (NCCL broadcast + frame gather)",
+                       "parallelism": f"views sharded over {world} GPU(s), scene replicated (one NCCL broadcast); frames collected on rank 0 by copy-engine pushes over NVLink into one CUDA-IPC frame array, inside the timed region",
                        "pipelining": "3 frames in flight (the reference keeps 2, SurfaceRenderer.h:66): the memory-bound front of the next frames overlaps the SM-bound blend of the current one; single_frame_latency_ms is one frame alone",
                        "l2_policy": "inputs larger than L2 (scene arrays 1.4 GB, pair buffers 0.4 GB vs 126 MB L2); a different view every step"},
             "pairs": int(stage_pairs), "visible": int(visible), "capacity_ok": bool(cap_ok),
@@ -413,7 +417,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_ms / e2e_steps / world, "unit": "ms/frame", "h2d_bytes_per_step": 136, "d2h_bytes_per_step": frame_bytes,
                     "steps": e2e_steps, "checksum": checksum, "serial_latency_ms": e2e_serial_ms / e2e_steps,
                     "frames_repeated": repeats,
-                    "scope": "rank-local: every rank delivers the frames of its own views into pinned host memory of the node (max over ranks / total frames); the NCCL gather of `value` is not on this path",
+                    "scope": "rank-local: every rank delivers the frames of its own views into pinned host memory of the node (max over ranks / total frames); the collection on rank 0 that `value` includes is not on this path",
                     "note": "lookAt on host -> rasterFrame -> drawAsync into pinned host memory, frames in flight as in the reference's loop"},
             # per frame: setup, preprocess, duplication, ranges, blend order, blend, 2 x histogram (+ plan) + one onesweep launch per
             # 8-bit digit of the widest possible key of each sort: 4 for the 32 depth bits (a pass whose digit is constant
@@ -425,8 +429,15 @@ def run_gpu(args):
             ms, cpu_pairs, cpu_stages, cores = cpu_frames(g, ubos[0], 3, 1)
             line["cpu_baseline"] = {"value": ms, "unit": "ms/frame", "cores": cores, "kind": "port",
                                     "sample": "3 full frames (after 1 warm-up) of the same 6M-Gaussian scene, view 0", "stages_ms": cpu_stages}
+    if shared is not None:
+        if rank == 0:   # every slot of the last round arrived
+            got = shared.tensor()
+            collected_ok = all(int(got[v, ::16, ::16, :3].amax().item()) > 0 for v in range(K * world))
+            line["config"]["frames_collected_on_rank0"] = f"{K * world} per round, all with pixels: {collected_ok}"
+            del got
+        shared.close()
     eng.close()
-    del frames, gathered
+    del frames
     torch.cuda.empty_cache()
     config5 = None if args.no_config5 else run_config5(E, torch, dist, world, rank, local_rank, dev, args.config5_collect)
     if rank == 0:
