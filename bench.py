@@ -39,7 +39,7 @@ SCENE_SEED = 3
 LOG_SCALE_MEAN = -5.2          # calibrated: P/N = 2.64 at 1080p (reference bicycle scene: 15.7 M pairs, demo/README.md:20)
 RING_VIEWS = 64                # cameras on a ring through the "garden" eye (2.8, 2.8, 2.6)
 RING_PHI, RING_RADIUS, RING_THETA0 = 0.9898, 4.7371, 0.7853982
-MIN_TIMED_S = 1.0              # device time the timed region must hold: the K-step loop is repeated until it does
+MIN_TIMED_S = 1.05              # device time the timed region must hold: the K-step loop is repeated until it does
 METRIC = "ms/frame 6M-Gaussian 1080p SH3"
 WORKLOAD = "synthetic 6M Gaussians (MipNeRF360-garden scale) SH3 at 1920x1080"
 
@@ -342,7 +342,10 @@ def run_gpu(args):
     hosts_np = [hbuf.numpy() for hbuf in hosts]
     copied = [torch.cuda.Event() for _ in range(NBUF)]
     cam = E.PerspectiveCamera(WIDTH, HEIGHT)
-    e2e_steps = min(K, 64)
+    # like `value`, over enough frames that the fill and drain of the pipeline (one frame's latency + one copy, ~1 ms) and a
+    # noisy neighbour do not decide the number: the K-step loop repeated until it holds >= ~0.5 s (e2e.steps says how many)
+    e2e_steps = K * max(1, rounds // 2)
+    serial_steps = min(K, 64)
     for s in range(3):
         cam.look_at(E.to_cartesian(*ring_camera_params(s * world + rank)), (0, 0, 0), (0, 0, 1))
         eng.raster_frame(cam, stream)
@@ -365,7 +368,7 @@ def run_gpu(args):
     checksum += int(hosts_np[(e2e_steps - 1) % NBUF][..., :3].sum())
     # and the same loop strictly serial (draw() blocks before the next rasterFrame): the latency of one frame end to end
     t0 = time.perf_counter()
-    for s in range(e2e_steps):
+    for s in range(serial_steps):
         cam.look_at(E.to_cartesian(*ring_camera_params((W + s) * world + rank)), (0, 0, 0), (0, 0, 1))
         eng.raster_frame(cam, stream)
         eng.draw(hosts_np[0])
@@ -415,7 +418,7 @@ def run_gpu(args):
                          "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": pass_ms,
                          "peak_source": peak_src},
             "e2e": {"value": e2e_ms / e2e_steps / world, "unit": "ms/frame", "h2d_bytes_per_step": 136, "d2h_bytes_per_step": frame_bytes,
-                    "steps": e2e_steps, "checksum": checksum, "serial_latency_ms": e2e_serial_ms / e2e_steps,
+                    "steps": e2e_steps, "checksum": checksum, "serial_latency_ms": e2e_serial_ms / serial_steps,
                     "frames_repeated": repeats,
                     "scope": "rank-local: every rank delivers the frames of its own views into pinned host memory of the node (max over ranks / total frames); the collection on rank 0 that `value` includes is not on this path",
                     "note": "lookAt on host -> rasterFrame -> drawAsync into pinned host memory, frames in flight as in the reference's loop"},
