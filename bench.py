@@ -253,20 +253,32 @@ def run_gpu(args):
     lib = tpdcu()
     # N > 1: the K * N frames of a round are collected on rank 0, slot = step * N + rank of ONE array in rank 0's HBM that every
     # rank has mapped (torpedo_b200.multiview.SharedFrames; the mapping is made here, once, like the scene broadcast)
-    shared = None
+    shared, gathered, collect = None, None, "none (one GPU)"
     if world > 1:
         from torpedo_b200 import multiview as mv
-        shared = mv.SharedFrames(K * world, HEIGHT, WIDTH, local_rank)
+        try:
+            shared = mv.SharedFrames(K * world, HEIGHT, WIDTH, local_rank)
+            collect = "copy-engine pushes over NVLink into one CUDA-IPC frame array on rank 0"
+        except mv.SharedFramesUnavailable as e:   # raised on every rank alike: NCCL gathers instead, and the line says so
+            gathered = [torch.zeros_like(frames) for _ in range(world)] if rank == 0 else None
+            collect = f"NCCL gathers, 4 frames per asynchronous chunk (CUDA IPC frame array unavailable: {e})"
+    GATHER_CHUNK = 4
 
     def render_steps(first_step, count, gather=False):
+        pending = []
         for s in range(count):
             view = (first_step + s) * world + rank
             if shared is None:
                 check(lib.tpdcu_bind_output_device_ptr(eng.ctx, frames[s].data_ptr(), WIDTH * 4))
                 eng.raster_ubo(ubos[view % RING_VIEWS], SH_DEGREE, stream)
+                if gather and world > 1 and ((s + 1) % GATHER_CHUNK == 0 or s + 1 == count):
+                    c0 = s + 1 - ((s % GATHER_CHUNK) + 1)
+                    pending.append(dist.gather(frames[c0:s + 1], [gt[c0:s + 1] for gt in gathered] if rank == 0 else None, dst=0, async_op=True))
             else:   # rendered into the engine's own target, pushed by a copy engine while the next frame renders
                 eng.raster_ubo(ubos[view % RING_VIEWS], SH_DEGREE, stream)
                 check(lib.tpdcu_read_frame_async(eng.ctx, shared.ptr_of_view(s * world + rank), WIDTH * 4, stream))
+        for work in pending:
+            work.wait()     # the current stream waits for the transfers; the host does not
         if shared is not None and gather:
             shared.fence()  # stream-ordered: behind it rank 0 holds every rank's frames of these steps
 
@@ -398,7 +410,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_gaussians": n, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
                        "views": f"ring of {RING_VIEWS} cameras through the garden eye, view = step*N + rank",
-                       "parallelism": f"views sharded over {world} GPU(s), scene replicated (one NCCL broadcast); frames collected on rank 0 by copy-engine pushes over NVLink into one CUDA-IPC frame array, inside the timed region",
+                       "parallelism": f"views sharded over {world} GPU(s), scene replicated (one NCCL broadcast); frames collected on rank 0 inside the timed region by: {collect}",
                        "pipelining": "3 frames in flight (the reference keeps 2, SurfaceRenderer.h:66): the memory-bound front of the next frames overlaps the SM-bound blend of the current one; single_frame_latency_ms is one frame alone",
                        "l2_policy": "inputs larger than L2 (scene arrays 1.4 GB, pair buffers 0.4 GB vs 126 MB L2); a different view every step"},
             "pairs": int(stage_pairs), "visible": int(visible), "capacity_ok": bool(cap_ok),
@@ -440,7 +452,7 @@ def run_gpu(args):
             del got
         shared.close()
     eng.close()
-    del frames
+    del frames, gathered
     torch.cuda.empty_cache()
     config5 = None if args.no_config5 else run_config5(E, torch, dist, world, rank, local_rank, dev, args.config5_collect)
     if rank == 0:
@@ -498,7 +510,12 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev, mode="push"):
     def render_batch(view_ids, out):
         render_to(view_ids, [out[k].data_ptr() for k in range(len(view_ids))])
 
-    shared = mv.SharedFrames(views, HEIGHT, WIDTH, local_rank) if mode in ("direct", "push") else None
+    shared, fallback = None, ""
+    if mode in ("direct", "push"):
+        try:
+            shared = mv.SharedFrames(views, HEIGHT, WIDTH, local_rank)
+        except mv.SharedFramesUnavailable as e:   # raised on every rank alike
+            mode, fallback = "gather", f" (asked for the CUDA-IPC frame array, unavailable: {e})"
     mid = torch.cuda.Event(enable_timing=True)
 
     def timed_render(fn):
@@ -552,7 +569,7 @@ def run_config5(E, torch, dist, world, rank, local_rank, dev, mode="push"):
         nonblack = [int((frames[v, ::8, ::8, :3].amax() > 0).item()) for v in range(views)]
         how = ("every rank's blend kernel stores its pixels straight into rank 0's frame array over NVLink (CUDA IPC mapping made once, "
                "outside the timed region, like the scene broadcast); one stream-ordered NCCL fence per batch" if mode == "direct" else
-               f"one NCCL gather per view slot straight into view order, {chunk} slots per asynchronous chunk")
+               f"one NCCL gather per view slot straight into view order, {chunk} slots per asynchronous chunk" + fallback)
         out = {"workload": "64-view batch of 3M Gaussians at 1080p sharded by view across N B200, frames collected on rank 0", "n_gaussians": n,
                "views": views, "n_gpus": world, "scaling": "strong", "ms_per_batch": ms, "ms_per_view": ms / views, "views_per_s": views / ms * 1e3,
                "batches_timed": len(times), "collect": mode, "gather": how,

@@ -45,6 +45,11 @@ def _worker(rank, world, port, n_views, result_path):
         chunked = mv.render_views(render_batch, n_views, 4, 6, dev, chunk=2)
         assert rendered == mv.views_of_rank(n_views, rank, world)
         assert (chunked is None) == (frames is None) and (frames is None or torch.equal(chunked, frames))
+        # the shared frame array needs CUDA IPC: without a GPU the owner's allocation fails, EVERY rank learns it through the
+        # same collectives and raises the same exception, and the caller falls back to the gathers above
+        with pytest.raises(mv.SharedFramesUnavailable) as unavailable:
+            mv.SharedFrames(n_views, 4, 6, 0)
+        assert "rank 0" in str(unavailable.value)
         if rank == 0:
             assert frames.shape == (n_views, 4, 6, 4)
             for v in range(n_views):

@@ -106,36 +106,69 @@ def render_views(render_batch: Callable[[Sequence[int], torch.Tensor], None], n_
     return out[:n_views] if rank == dst else None
 
 
+class SharedFramesUnavailable(RuntimeError):
+    """CUDA IPC could not map the frame array into every rank (raised on EVERY rank alike): collect with `render_views`."""
+
+
 class SharedFrames:
     """The batch's (n_views, H, W, 4) uint8 frame array, living in `dst`'s HBM and mapped into every rank of the box.
 
     The gather above costs the collecting GPU twice: NCCL's receive kernels take SMs away from its own views, and the last
-    chunk's transfer trails the last frame. Here nothing is gathered: rank r binds slot v of this array as the render target
-    of its view v (`ptr_of_view`), the blend kernel's pixel stores cross NVLink / NVSwitch as they are produced, and the only
-    collective left is the completion fence. Set up once per (batch shape, process group) — an IPC handle exchange and a
-    peer mapping — like the scene broadcast; `include/tpdcu.h` (tpdcu_ipc_frames_*) is the ABI underneath.
+    chunk's transfer trails the last frame. Here nothing is gathered: rank r writes its view v into slot v of this array
+    (`ptr_of_view`) — either by pushing the finished frame with `tpdcu_read_frame_async` (a copy engine moves it over NVLink /
+    NVSwitch while the next view renders: the fastest at every N measured) or by binding the slot as the render
+    target, so that the blend kernel's pixel stores cross the link as they are produced (as fast up to 4 GPUs; at 8 the seven
+    senders stall on their fine-grained stores) — and the only collective left is the completion fence. Set up once per
+    (batch shape, process group) — an IPC handle exchange and a peer mapping — like the scene broadcast;
+    `include/tpdcu.h` (tpdcu_ipc_frames_*) is the ABI underneath. Raises SharedFramesUnavailable on every rank alike when
+    the mapping cannot be made (no peer access, IPC forbidden in the container).
     """
 
     def __init__(self, n_views: int, height: int, width: int, device_index: int, dst: int = 0):
         import ctypes as C
 
-        from ._lib import check, tpdcu
+        from ._lib import TpdError, check, tpdcu
         self._lib, self._check = tpdcu(), check
         self.world, self.rank = _world_rank()
         self.n_views, self.height, self.width, self.dst, self.device_index = n_views, height, width, dst, device_index
         self.frame_bytes = height * width * 4
         self.owner = self.rank == dst
         self._ptr = C.c_void_p()
+        self._fence = None
         handle = (C.c_ubyte * 64)()
+        # Every rank goes through the same collectives whether its own step worked or not, and all of them agree on the outcome:
+        # either every rank holds a mapping or none does and all raise SharedFramesUnavailable (callers fall back to the gathers).
+        problem = ""
         if self.owner:
-            check(self._lib.tpdcu_ipc_frames_create(device_index, n_views * self.frame_bytes, C.byref(self._ptr), handle))
-        box = [bytes(handle)]
+            try:
+                check(self._lib.tpdcu_ipc_frames_create(device_index, n_views * self.frame_bytes, C.byref(self._ptr), handle))
+            except TpdError as e:
+                problem = f"rank {self.rank}: {e}"
+        box = [bytes(handle), problem]
         if self.world > 1:
             dist.broadcast_object_list(box, src=dst)
-        if not self.owner:
+        problem = box[1]
+        if not self.owner and not problem:
             raw = (C.c_ubyte * 64).from_buffer_copy(box[0])
-            check(self._lib.tpdcu_ipc_frames_open(device_index, raw, C.byref(self._ptr)))
-        self._fence = None
+            try:
+                check(self._lib.tpdcu_ipc_frames_open(device_index, raw, C.byref(self._ptr)))
+            except TpdError as e:
+                problem = f"rank {self.rank}: {e}"
+        if self.world > 1:
+            problems = [None] * self.world
+            dist.all_gather_object(problems, problem)
+            problem = next((p for p in problems if p), "")
+        if problem:
+            self._release()
+            raise SharedFramesUnavailable(problem)
+
+    def _release(self) -> None:
+        if self._ptr.value:
+            if self.owner:
+                self._check(self._lib.tpdcu_ipc_frames_destroy(self.device_index, self._ptr))
+            else:
+                self._check(self._lib.tpdcu_ipc_frames_close(self.device_index, self._ptr))
+            self._ptr.value = None
 
     def ptr_of_view(self, view: int) -> int:
         if not (0 <= view < self.n_views):
@@ -170,11 +203,7 @@ class SharedFrames:
                 torch.cuda.synchronize(self.device_index)
                 if dist.get_backend() == "nccl":
                     dist.barrier()
-            if self.owner:
-                self._check(self._lib.tpdcu_ipc_frames_destroy(self.device_index, self._ptr))
-            else:
-                self._check(self._lib.tpdcu_ipc_frames_close(self.device_index, self._ptr))
-            self._ptr.value = None
+            self._release()
 
 
 def render_views_direct(render_to: Callable[[Sequence[int], Sequence[int]], None], shared: SharedFrames) -> None:
