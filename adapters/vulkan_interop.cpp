@@ -1,6 +1,8 @@
 // adapters/vulkan_interop.cpp — the Vulkan side of the frame hand-off.
 //
-// NOT COMPILED IN THIS IMAGE: there are no Vulkan headers, loader or ICD here or on the GPU boxes. The CUDA half of every
+// NOT BUILT OR RUN IN THIS IMAGE: there are no Vulkan headers, loader or ICD here or on the GPU boxes. What is checked: the file
+// compiles warning-free against declarations of the Vulkan symbols it uses (tests/cpp/vulkan_stub, written from the specification;
+// tests/test_adapter_syntax.py) and its object references tpdcu_bind_output_fd of include/tpdcu.h. The CUDA half of every
 // call below is executed by tests/test_external_memory_gpu.py (an opaque POSIX fd exported by the CUDA driver's VMM API is
 // imported through tpdcu_bind_output_fd and a frame is rendered into it); this file is the other half, written against
 // plain vulkan.h so that it does not depend on the Vulkan-Hpp version torpedo pins. Build it inside torpedo with
