@@ -410,7 +410,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "n_gaussians": n, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
                        "views": f"ring of {RING_VIEWS} cameras through the garden eye, view = step*N + rank",
-                       "parallelism": f"views sharded over {world} GPU(s), scene replicated (one NCCL broadcast); frames collected on rank 0 inside the timed region by: {collect}",
+                       "parallelism": "one GPU" if world == 1 else f"views sharded over {world} GPUs, scene replicated (one NCCL broadcast); frames collected on rank 0 inside the timed region by: {collect}",
                        "pipelining": "3 frames in flight (the reference keeps 2, SurfaceRenderer.h:66): the memory-bound front of the next frames overlaps the SM-bound blend of the current one; single_frame_latency_ms is one frame alone",
                        "l2_policy": "inputs larger than L2 (scene arrays 1.4 GB, pair buffers 0.4 GB vs 126 MB L2); a different view every step"},
             "pairs": int(stage_pairs), "visible": int(visible), "capacity_ok": bool(cap_ok),
