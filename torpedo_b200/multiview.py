@@ -2,9 +2,10 @@
 
 The Gaussian set is replicated (one broadcast), independent camera views are partitioned round-robin
 (view v -> rank v mod world), every rank renders its own views with its own GaussianEngine, and the frames are
-gathered on rank 0. There is no data-path collective inside a frame: the path does not shard within a frame
-(global scan + global sort), it shards across views. The functions here only move bytes with torch.distributed —
-NCCL on the GPU box, gloo in the CPU tests — and never render anything themselves.
+collected on rank 0 — pushed or stored into one frame array in rank 0's HBM that every process has mapped
+(`SharedFrames`, the fast path on a GPU box) or gathered with the process group's collectives (`render_views`, the
+generic path: NCCL without peer mappings, gloo in the CPU tests). There is no data-path collective inside a frame: the
+path does not shard within a frame (global scan + global sort), it shards across views. Nothing here renders.
 """
 from __future__ import annotations
 
@@ -207,9 +208,12 @@ class SharedFrames:
 
 
 def render_views_direct(render_to: Callable[[Sequence[int], Sequence[int]], None], shared: SharedFrames) -> None:
-    """Shard the views like `render_views`, but let `render_to(view_ids, target_ptrs)` render each view straight into its slot
-    of the shared frame array; ends with the completion fence. On return (stream-ordered on NCCL) `shared.tensor()` on the
-    collecting rank holds the batch in view order."""
+    """Shard the views like `render_views`, but let `render_to(view_ids, target_ptrs)` deliver each view straight into its slot
+    of the shared frame array (push the finished frame with tpdcu_read_frame_async, or bind the slot as the render target);
+    ends with the completion fence. On return (stream-ordered on NCCL) `shared.tensor()` on the collecting rank holds the
+    batch in view order. A frame whose pair buffers overflowed is only repeated by the engine's next finish(), into the
+    engine's own target: callers that cannot rule that out by a warm-up over their views check `frames_repeated()` after the
+    batch and deliver those views again."""
     mine = views_of_rank(shared.n_views, shared.rank, shared.world)
     if mine:
         render_to(mine, [shared.ptr_of_view(v) for v in mine])
