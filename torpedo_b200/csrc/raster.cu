@@ -316,6 +316,11 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     uint16_t v;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
@@ -324,6 +329,12 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
 
 #ifndef TPDCU_BLEND_FAST_DIRECTION
 #define TPDCU_BLEND_FAST_DIRECTION true
+#endif
+#ifndef TPDCU_BLEND_GROUPS
+#define TPDCU_BLEND_GROUPS 1
+#endif
+#ifndef TPDCU_BLEND_PIN_SMEM_BASES
+#define TPDCU_BLEND_PIN_SMEM_BASES 1
 #endif
 #ifndef TPDCU_BLEND_MINB
 #define TPDCU_BLEND_MINB 7
@@ -356,10 +367,15 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
     const float NEG_INF = __int_as_float(0xff800000);
     float u0 = (inside & 1u) ? 0.0f : NEG_INF, u1 = (inside & 2u) ? 0.0f : NEG_INF;
     uint32_t ent_s = (uint32_t)__cvta_generic_to_shared(&sm.ent[0]);
-    const uint32_t list_s = (uint32_t)__cvta_generic_to_shared(&sm.list[warp][0]);
+    uint32_t list_s = (uint32_t)__cvta_generic_to_shared(&sm.list[warp][0]);
     // ptxas would otherwise re-derive these three loop invariants inside the drain loop (5 instructions per 2 splats)
     // to save registers; a value that went through a shuffle cannot be rematerialised.
     ent_s = __shfl_sync(0xffffffffu, ent_s, lane);
+#if TPDCU_BLEND_PIN_SMEM_BASES
+    // ... and the shuffle of a uniform value by the own lane IS folded away: ptxas re-derived both shared-window addresses
+    // inside the drain loop (S2R SR_CgaCtaId, MOV, LEA, IMAD, IADD3 per two splats). An empty asm with read-write operands is opaque.
+    asm volatile("" : "+r"(ent_s), "+r"(list_s));
+#endif
     fx0 = __shfl_sync(0xffffffffu, fx0, lane);
     fy0 = __shfl_sync(0xffffffffu, fy0, lane);
     float T0 = 1.0f, T1 = 1.0f, r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
@@ -447,11 +463,9 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
 
         // ---- drain: front-to-back compositing (blend.slang:77-100) over this quadrant's list --------------------------
         const uint32_t my_ln = warp == 0 ? ln[0] : warp == 1 ? ln[1] : warp == 2 ? ln[2] : ln[3];
-#pragma unroll 2
-        for (uint32_t j = 0; j < my_ln; ++j) {
-            // the whole quadrant is done (uniform branch)
-            if ((j & 7u) == 0u && __all_sync(0xffffffffu, u0 < 0.0f && u1 < 0.0f)) break;
-            const uint32_t e = ent_s + lds_u16(list_s + 2u * j);
+        // one splat of the quadrant's list against this lane's two pixels; `off` = byte offset of its queue entry
+        auto composite = [&](uint32_t off) {
+            const uint32_t e = ent_s + off;
             const float4 q0 = lds_f4(e);
             const float4 q1 = lds_f4(e + 16u);
             const float dx0 = q0.x - fx0, dy = q0.y - fy0;
@@ -464,7 +478,7 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
             // branch (re)convergence would cost more than the arithmetic it skips.
             const bool h0 = p0 <= u0 && p0 >= q1.z;    // below the threshold alpha < 1/255 (blend.slang:89)
             const bool h1 = p1 <= u1 && p1 >= q1.z;
-            if (!(h0 || h1)) continue;
+            if (!(h0 || h1)) return;
             const float4 c = lds_f4(e + 32u);
             const float a0 = fminf(0.99f, q1.y * ex2_approx(p0)), a1 = fminf(0.99f, q1.y * ex2_approx(p1));
             const float w0 = a0 * T0, w1 = a1 * T1;
@@ -478,6 +492,28 @@ __global__ void __launch_bounds__(BLEND_THREADS, TPDCU_BLEND_MINB) blend_kernel(
             r1 = fmaf(c.x, m1, r1); g1 = fmaf(c.y, m1, g1); b1 = fmaf(c.z, m1, b1);
             T0 = s0 ? t0 : T0;
             T1 = s1 ? t1 : T1;
+        };
+        // Groups of eight splats: one vote whether the whole quadrant is done (uniform branch), ONE 16-byte load of the eight list
+        // entries, eight bodies back to back with no loop control between them (the rolled loop spent 5.5 of its ~26 common-path
+        // instructions per splat on the counter, the every-eighth test and the 16-bit list load); the last < 8 splats one by one.
+        uint32_t j = 0;
+        bool quadrant_done = false;
+#if TPDCU_BLEND_GROUPS
+        for (; j + 8u <= my_ln; j += 8u) {
+            if (__all_sync(0xffffffffu, u0 < 0.0f && u1 < 0.0f)) { quadrant_done = true; break; }
+            const uint4 offs = lds_u4(list_s + 2u * j);
+            composite(offs.x & 0xffffu); composite(offs.x >> 16);
+            composite(offs.y & 0xffffu); composite(offs.y >> 16);
+            composite(offs.z & 0xffffu); composite(offs.z >> 16);
+            composite(offs.w & 0xffffu); composite(offs.w >> 16);
+        }
+#endif
+        if (!quadrant_done && j < my_ln) {
+#pragma unroll 2
+            for (; j < my_ln; ++j) {
+                if ((j & 7u) == 0u && __all_sync(0xffffffffu, u0 < 0.0f && u1 < 0.0f)) break;
+                composite(lds_u16(list_s + 2u * j));
+            }
         }
         // block vote (blend.slang:56-63); also the barrier that lets the queue be refilled
         const bool finished = in >= range.y;
