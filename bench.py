@@ -441,9 +441,10 @@ def run_gpu(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            ms, cpu_pairs, cpu_stages, cores = cpu_frames(g, ubos[0], 3, 1)
+            CPU_FRAMES = 16   # ~9 s of CPU work on 16 cores: a bounded sample of the same workload
+            ms, cpu_pairs, cpu_stages, cores = cpu_frames(g, ubos[0], CPU_FRAMES, 1)
             line["cpu_baseline"] = {"value": ms, "unit": "ms/frame", "cores": cores, "kind": "port",
-                                    "sample": "3 full frames (after 1 warm-up) of the same 6M-Gaussian scene, view 0", "stages_ms": cpu_stages}
+                                    "sample": f"{CPU_FRAMES} full frames (after 1 warm-up) of the same 6M-Gaussian scene, view 0", "stages_ms": cpu_stages}
     if shared is not None:
         if rank == 0:   # every slot of the last round arrived
             got = shared.tensor()
